@@ -1,0 +1,539 @@
+/*
+ * oracle/smle_oracle_impl.h -- value-type-generic body of the CPU oracle.
+ *
+ * TEST INFRASTRUCTURE ONLY (see smle_oracle.c header).  Included twice by
+ * smle_oracle.c with
+ *     VT   = double / float
+ *     SFX  = f64 / f32
+ * Each function cites the reference file:line (under /root/reference) whose
+ * algorithm it restates.  Nothing here is copied; every loop is re-derived
+ * from the behaviour described in SURVEY.md section 8(a).
+ */
+
+#define ORC_CAT_(a, b) a##_##b
+#define ORC_CAT(a, b) ORC_CAT_(a, b)
+#define FN(name) ORC_CAT(name, SFX)
+
+/* ------------------------------------------------------------------ */
+/* Serial gold SpMV: y_out = beta*y_in + alpha*A*x                      */
+/* restates work_2025/spmm/sample.hpp:11-34 (== cpu_spmv.cpp:245-265)   */
+/* ------------------------------------------------------------------ */
+void FN(orc_spmv_gold)(int m, const int *ro, const int *ci, const VT *va,
+                       const VT *x, const VT *y_in, VT *y_out, VT alpha, VT beta)
+{
+    for (int r = 0; r < m; ++r) {
+        VT acc = beta * y_in[r];
+        for (int o = ro[r]; o < ro[r + 1]; ++o)
+            acc += alpha * va[o] * x[ci[o]];
+        y_out[r] = acc;
+    }
+}
+
+/* ------------------------------------------------------------------ */
+/* Merge-path SpMV with T shares + serial carry fix-up                  */
+/* restates cpu_spmv.cpp:360-421 (OmpMergeCsrmv)                        */
+/*  - shares of ceil((m+nnz)/T) merge items (:379-386)                  */
+/*  - whole rows (:392-401), trailing partial row (:404-408)            */
+/*  - carry arrays are fixed [256] in the reference (:370-371)          */
+/*  - fix-up runs over tid < T-1 only (:416-420)                        */
+/* returns 0, or -1 when T exceeds the reference's 256-entry carry array */
+/* ------------------------------------------------------------------ */
+int FN(orc_merge_csrmv)(int T, int m, int nnz, const int *row_end, const int *ci,
+                        const VT *va, const VT *x, VT *y)
+{
+    if (T < 1 || T > 256) return -1;
+    int carry_row[256];
+    VT carry_val[256];
+
+#pragma omp parallel for schedule(static) num_threads(T)
+    for (int tid = 0; tid < T; ++tid) {
+        int total = m + nnz;
+        int share = (total + T - 1) / T;
+        int d0 = share * tid < total ? share * tid : total;
+        int d1 = d0 + share < total ? d0 + share : total;
+        int c0[2], c1[2];
+        orc_merge_path_search(d0, row_end, m, nnz, c0);
+        orc_merge_path_search(d1, row_end, m, nnz, c1);
+        int r = c0[0], z = c0[1];
+        for (; r < c1[0]; ++r) {
+            VT acc = 0.0;
+            for (; z < row_end[r]; ++z)
+                acc += va[z] * x[ci[z]];
+            y[r] = acc;
+        }
+        VT tail = 0.0;
+        for (; z < c1[1]; ++z)
+            tail += va[z] * x[ci[z]];
+        carry_row[tid] = c1[0];
+        carry_val[tid] = tail;
+    }
+    for (int tid = 0; tid < T - 1; ++tid)
+        if (carry_row[tid] < m)
+            y[carry_row[tid]] += carry_val[tid];
+    return 0;
+}
+
+/* ------------------------------------------------------------------ */
+/* Merge-path SpMM, X (n x k) and Y (m x k) row-major                   */
+/* restates work_2025/spmm/merge_based.hpp:49-153 (OmpMergeCsrmm)       */
+/*  - heap carry-out T x k (:60-61); fix-up over ALL tid with           */
+/*    row < m guard (:138-149)                                          */
+/* ------------------------------------------------------------------ */
+void FN(orc_merge_csrmm)(int T, int m, int nnz, const int *row_end, const int *ci,
+                         const VT *va, const VT *X, VT *Y, int k)
+{
+    int *carry_row = (int *)malloc(sizeof(int) * (size_t)T);
+    VT *carry_val = (VT *)malloc(sizeof(VT) * (size_t)T * (size_t)k);
+
+#pragma omp parallel for schedule(static) num_threads(T)
+    for (int tid = 0; tid < T; ++tid) {
+        int total = m + nnz;
+        int share = (total + T - 1) / T;
+        int d0 = share * tid < total ? share * tid : total;
+        int d1 = d0 + share < total ? d0 + share : total;
+        int c0[2], c1[2];
+        orc_merge_path_search(d0, row_end, m, nnz, c0);
+        orc_merge_path_search(d1, row_end, m, nnz, c1);
+        VT *acc = (VT *)malloc(sizeof(VT) * (size_t)k);
+        for (int i = 0; i < k; ++i) acc[i] = 0.0;
+        int r = c0[0], z = c0[1];
+        for (; r < c1[0]; ++r) {
+            for (; z < row_end[r]; ++z) {
+                VT v = va[z];
+                const VT *xr = X + ci[z] * k; /* int product, as merge_based.hpp:97 */
+                for (int i = 0; i < k; ++i) acc[i] += v * xr[i];
+            }
+            VT *yr = Y + r * k; /* merge_based.hpp:106 */
+            for (int i = 0; i < k; ++i) { yr[i] = acc[i]; acc[i] = 0.0; }
+        }
+        for (; z < c1[1]; ++z) {
+            VT v = va[z];
+            const VT *xr = X + ci[z] * k;
+            for (int i = 0; i < k; ++i) acc[i] += v * xr[i];
+        }
+        carry_row[tid] = c1[0];
+        for (int i = 0; i < k; ++i) carry_val[(size_t)tid * k + i] = acc[i];
+        free(acc);
+    }
+    for (int tid = 0; tid < T; ++tid) {
+        int r = carry_row[tid];
+        if (r < m)
+            for (int i = 0; i < k; ++i)
+                Y[r * k + i] += carry_val[(size_t)tid * k + i];
+    }
+    free(carry_val);
+    free(carry_row);
+}
+
+/* ------------------------------------------------------------------ */
+/* Even-nnz split SpMM                                                  */
+/* restates work_2025/spmm/nonzero_splitting.hpp:52-150 and its         */
+/* RowPathSearch (:19-44): x = first row whose end offset > y-1         */
+/* ------------------------------------------------------------------ */
+static int FN(orc_row_path_search)(const int *row_end, int m, int y)
+{
+    if (y == 0) return 0;
+    int lo = 0, hi = m;
+    while (lo < hi) {
+        int mid = (lo + hi) >> 1;
+        if (row_end[mid] <= y - 1) lo = mid + 1; else hi = mid;
+    }
+    return lo < m ? lo : m;
+}
+
+void FN(orc_nonzero_split_csrmm)(int T, int m, int nnz, const int *row_end, const int *ci,
+                                 const VT *va, const VT *X, VT *Y, int k)
+{
+    int *carry_row = (int *)malloc(sizeof(int) * (size_t)T);
+    VT *carry_val = (VT *)malloc(sizeof(VT) * (size_t)T * (size_t)k);
+
+#pragma omp parallel for schedule(static) num_threads(T)
+    for (int tid = 0; tid < T; ++tid) {
+        int share = (nnz + T - 1) / T;
+        int z = share * tid < nnz ? share * tid : nnz;
+        int z1 = z + share < nnz ? z + share : nnz;
+        int r = FN(orc_row_path_search)(row_end, m, z);
+        int r1 = FN(orc_row_path_search)(row_end, m, z1);
+        VT *acc = (VT *)malloc(sizeof(VT) * (size_t)k);
+        for (int i = 0; i < k; ++i) acc[i] = 0.0;
+        for (; r < r1; ++r) {
+            for (; z < row_end[r]; ++z) {
+                VT v = va[z];
+                const VT *xr = X + ci[z] * k;
+                for (int i = 0; i < k; ++i) acc[i] += v * xr[i];
+            }
+            VT *yr = Y + r * k;
+            for (int i = 0; i < k; ++i) { yr[i] = acc[i]; acc[i] = 0.0; }
+        }
+        for (; z < z1; ++z) {
+            VT v = va[z];
+            const VT *xr = X + ci[z] * k;
+            for (int i = 0; i < k; ++i) acc[i] += v * xr[i];
+        }
+        carry_row[tid] = r1;
+        for (int i = 0; i < k; ++i) carry_val[(size_t)tid * k + i] = acc[i];
+        free(acc);
+    }
+    for (int tid = 0; tid < T; ++tid) {
+        int r = carry_row[tid];
+        if (r < m)
+            for (int i = 0; i < k; ++i)
+                Y[r * k + i] += carry_val[(size_t)tid * k + i];
+    }
+    free(carry_val);
+    free(carry_row);
+}
+
+/* ------------------------------------------------------------------ */
+/* Row-split SpMM  -- restates work_2025/spmm/row_splitting.hpp:18-54   */
+/* ------------------------------------------------------------------ */
+void FN(orc_row_split_csrmm)(int T, int m, const int *ro, const int *ci, const VT *va,
+                             const VT *X, VT *Y, int k)
+{
+#pragma omp parallel for schedule(static) num_threads(T)
+    for (int r = 0; r < m; ++r) {
+        VT *acc = (VT *)alloca(sizeof(VT) * (size_t)k);
+        for (int i = 0; i < k; ++i) acc[i] = 0.0;
+        for (int o = ro[r]; o < ro[r + 1]; ++o) {
+            VT v = va[o];
+            const VT *xr = X + ci[o] * k;
+            for (int i = 0; i < k; ++i) acc[i] += v * xr[i];
+        }
+        for (int i = 0; i < k; ++i) Y[r * k + i] = acc[i];
+    }
+}
+
+/* ------------------------------------------------------------------ */
+/* Single-RHS CG building blocks                                        */
+/* restate work_2025/main/single_strategy.hpp:29-55 (row-parallel SpMV),*/
+/* :61-70 (dot), :76-83 (axpy), :90-97 (p update)                       */
+/* ------------------------------------------------------------------ */
+static void FN(orc_row_spmv)(int m, const int *ro, const int *ci, const VT *va,
+                             const VT *x, VT *y)
+{
+#pragma omp parallel for schedule(static)
+    for (int r = 0; r < m; ++r) {
+        VT s = 0.0;
+        for (int o = ro[r]; o < ro[r + 1]; ++o) s += va[o] * x[ci[o]];
+        y[r] = s;
+    }
+}
+
+static VT FN(orc_dot)(int n, const VT *a, const VT *b)
+{
+    VT s = 0.0;
+#pragma omp parallel for reduction(+ : s)
+    for (int i = 0; i < n; ++i) s += a[i] * b[i];
+    return s;
+}
+
+static void FN(orc_axpy)(int n, VT a, const VT *x, VT *y)
+{
+#pragma omp parallel for
+    for (int i = 0; i < n; ++i) y[i] += a * x[i];
+}
+
+static void FN(orc_update_p)(int n, const VT *r, VT beta, VT *p)
+{
+#pragma omp parallel for
+    for (int i = 0; i < n; ++i) p[i] = r[i] + beta * p[i];
+}
+
+/* ------------------------------------------------------------------ */
+/* Single-RHS CG -- restates single_strategy.hpp:105-170                */
+/*  x0 = 0, r = p = b; test sqrt(r.r)/||b|| < tol BEFORE the p update;  */
+/*  returned count includes the converging iteration (:152-156);        */
+/*  ||b|| == 0 is replaced by 1 (:130-131).                             */
+/* ------------------------------------------------------------------ */
+int FN(orc_cg_single)(int n, const int *ro, const int *ci, const VT *va,
+                      const VT *b, VT *x, int max_iters, VT tol)
+{
+    VT *r = (VT *)malloc(sizeof(VT) * (size_t)n);
+    VT *p = (VT *)malloc(sizeof(VT) * (size_t)n);
+    VT *Ap = (VT *)malloc(sizeof(VT) * (size_t)n);
+#pragma omp parallel for
+    for (int i = 0; i < n; ++i) { x[i] = 0.0; r[i] = b[i]; p[i] = b[i]; }
+
+    VT rs_old = FN(orc_dot)(n, r, r);
+    VT b_norm = (VT)sqrt((double)FN(orc_dot)(n, b, b));
+    if (b_norm == 0.0) b_norm = 1.0;
+
+    int it = 0;
+    for (; it < max_iters; ++it) {
+        FN(orc_row_spmv)(n, ro, ci, va, p, Ap);
+        VT pAp = FN(orc_dot)(n, p, Ap);
+        VT alpha = rs_old / pAp;
+        FN(orc_axpy)(n, alpha, p, x);
+        FN(orc_axpy)(n, -alpha, Ap, r);
+        VT rs_new = FN(orc_dot)(n, r, r);
+        if ((VT)sqrt((double)rs_new) / b_norm < tol) { ++it; break; }
+        VT beta = rs_new / rs_old;
+        FN(orc_update_p)(n, r, beta, p);
+        rs_old = rs_new;
+    }
+    free(r); free(p); free(Ap);
+    return it;
+}
+
+/* ------------------------------------------------------------------ */
+/* Multi-RHS helpers -- restate work_2025/cg/utils_multiple.hpp:9-24,   */
+/* :28-42, :45-59 (row-major n x k blocks, per-column scalars)          */
+/* ------------------------------------------------------------------ */
+static void FN(orc_dot_multi)(int n, int k, const VT *X, const VT *Y, VT *out)
+{
+    int nt = omp_get_max_threads();
+    VT *part = (VT *)calloc((size_t)nt * (size_t)k, sizeof(VT));
+#pragma omp parallel
+    {
+        VT *mine = part + (size_t)omp_get_thread_num() * k;
+#pragma omp for schedule(static)
+        for (int j = 0; j < n; ++j) {
+            const VT *xr = X + (long long)j * k;
+            const VT *yr = Y + (long long)j * k;
+            for (int i = 0; i < k; ++i) mine[i] += xr[i] * yr[i];
+        }
+    }
+    for (int i = 0; i < k; ++i) out[i] = 0.0;
+    for (int t = 0; t < nt; ++t)
+        for (int i = 0; i < k; ++i) out[i] += part[(size_t)t * k + i];
+    free(part);
+}
+
+static void FN(orc_axpy_multi)(int n, int k, const VT *a, const VT *X, VT *Y)
+{
+#pragma omp parallel for
+    for (int j = 0; j < n; ++j) {
+        const VT *xr = X + (long long)j * k;
+        VT *yr = Y + (long long)j * k;
+        for (int i = 0; i < k; ++i) yr[i] += a[i] * xr[i];
+    }
+}
+
+static void FN(orc_update_p_multi)(int n, int k, const VT *R, const VT *beta, VT *P)
+{
+#pragma omp parallel for
+    for (int j = 0; j < n; ++j) {
+        const VT *rr = R + (long long)j * k;
+        VT *pr = P + (long long)j * k;
+        for (int i = 0; i < k; ++i) pr[i] = rr[i] + beta[i] * pr[i];
+    }
+}
+
+/* ------------------------------------------------------------------ */
+/* Multi-RHS CG -- restates work_2025/main/no_pretreatment.hpp:35-197   */
+/*  k independent recurrences in lock-step; converged[i] latches and    */
+/*  forces alpha=beta=0 (:109-120, :165-176); stops when all latched;   */
+/*  max relative error per iteration is recorded (:133-155).            */
+/*  kernel: 0 SIMPLE(row split) 1 MERGE 2 NONZERO_SPLIT (types.hpp:11)  */
+/*  T = g_omp_threads of the reference (hyper_parameters.hpp:11).       */
+/*  hist (nullable) receives up to max_iters doubles, *hist_len count.  */
+/* ------------------------------------------------------------------ */
+int FN(orc_cg_multi)(int T, int n, int nnz, const int *ro, const int *ci, const VT *va,
+                     const VT *B, VT *X, int k, int max_iters, VT tol, int kernel,
+                     double *hist, int *hist_len)
+{
+    size_t nk = (size_t)n * (size_t)k;
+    VT *R = (VT *)malloc(sizeof(VT) * nk);
+    VT *P = (VT *)malloc(sizeof(VT) * nk);
+    VT *AP = (VT *)malloc(sizeof(VT) * nk);
+    VT *alpha = (VT *)malloc(sizeof(VT) * (size_t)k);
+    VT *beta = (VT *)malloc(sizeof(VT) * (size_t)k);
+    VT *rs_old = (VT *)malloc(sizeof(VT) * (size_t)k);
+    VT *rs_new = (VT *)malloc(sizeof(VT) * (size_t)k);
+    VT *pAp = (VT *)malloc(sizeof(VT) * (size_t)k);
+    VT *bn = (VT *)malloc(sizeof(VT) * (size_t)k);
+    char *done = (char *)calloc((size_t)k, 1);
+
+#pragma omp parallel for
+    for (long long i = 0; i < (long long)nk; ++i) { X[i] = 0.0; R[i] = B[i]; P[i] = B[i]; }
+
+    FN(orc_dot_multi)(n, k, B, B, bn);
+    for (int i = 0; i < k; ++i) {
+        bn[i] = (VT)sqrt((double)bn[i]);
+        if (bn[i] == 0.0) bn[i] = 1.0;
+    }
+    FN(orc_dot_multi)(n, k, R, R, rs_old);
+    int nh = 0;
+
+    int it;
+    for (it = 0; it < max_iters; ++it) {
+        memset(AP, 0, sizeof(VT) * nk); /* no_pretreatment.hpp:93 */
+        if (kernel == 0)
+            FN(orc_row_split_csrmm)(T, n, ro, ci, va, P, AP, k);
+        else if (kernel == 1)
+            FN(orc_merge_csrmm)(T, n, nnz, ro + 1, ci, va, P, AP, k);
+        else
+            FN(orc_nonzero_split_csrmm)(T, n, nnz, ro + 1, ci, va, P, AP, k);
+
+        FN(orc_dot_multi)(n, k, P, AP, pAp);
+        for (int i = 0; i < k; ++i) alpha[i] = done[i] ? (VT)0.0 : rs_old[i] / pAp[i];
+        FN(orc_axpy_multi)(n, k, alpha, P, X);
+        for (int i = 0; i < k; ++i) alpha[i] = -alpha[i];
+        FN(orc_axpy_multi)(n, k, alpha, AP, R);
+        FN(orc_dot_multi)(n, k, R, R, rs_new);
+
+        int ndone = 0;
+        double worst = 0.0;
+        for (int i = 0; i < k; ++i) {
+            double rel = sqrt((double)rs_new[i]) / (double)bn[i];
+            if (rel > worst) worst = rel;
+            if (!done[i] && rel < (double)tol) done[i] = 1;
+            if (done[i]) ++ndone;
+        }
+        if (hist) hist[nh] = worst;
+        ++nh;
+        if (ndone == k) { ++it; break; }
+
+        for (int i = 0; i < k; ++i) beta[i] = done[i] ? (VT)0.0 : rs_new[i] / rs_old[i];
+        FN(orc_update_p_multi)(n, k, R, beta, P);
+        for (int i = 0; i < k; ++i) rs_old[i] = rs_new[i];
+    }
+    if (hist_len) *hist_len = nh;
+    free(R); free(P); free(AP); free(alpha); free(beta); free(rs_old); free(rs_new);
+    free(pAp); free(bn); free(done);
+    return it;
+}
+
+/* ------------------------------------------------------------------ */
+/* COO -> CSR, as CsrMatrix::Init (sparse_matrix.h:668-733):            */
+/* stable sort by (row, col), duplicates kept, then offsets fill.       */
+/* Input COO arrays are consumed (sorted in place via a scratch copy).  */
+/* ------------------------------------------------------------------ */
+typedef struct { int row, col; VT val; } FN(orc_coo);
+
+static void FN(orc_coo_stable_sort)(FN(orc_coo) *t, size_t n)
+{
+    /* bottom-up merge sort: stable, same ordering as std::stable_sort with
+       CooComparator (sparse_matrix.h:636-643) */
+    FN(orc_coo) *tmp = (FN(orc_coo) *)malloc(sizeof(*tmp) * (n ? n : 1));
+    FN(orc_coo) *src = t, *dst = tmp;
+    for (size_t w = 1; w < n; w <<= 1) {
+#pragma omp parallel for schedule(dynamic, 1)
+        for (long long lo0 = 0; lo0 < (long long)n; lo0 += (long long)(2 * w)) {
+            size_t lo = (size_t)lo0;
+            size_t mid = lo + w < n ? lo + w : n;
+            size_t hi = lo + 2 * w < n ? lo + 2 * w : n;
+            size_t i = lo, j = mid, o = lo;
+            while (i < mid && j < hi) {
+                int take_right = (src[j].row < src[i].row) ||
+                                 (src[j].row == src[i].row && src[j].col < src[i].col);
+                dst[o++] = take_right ? src[j++] : src[i++];
+            }
+            while (i < mid) dst[o++] = src[i++];
+            while (j < hi) dst[o++] = src[j++];
+        }
+        FN(orc_coo) *sw = src; src = dst; dst = sw;
+    }
+    if (src != t) memcpy(t, src, sizeof(*t) * n);
+    free(tmp);
+}
+
+static void FN(orc_coo_to_csr)(FN(orc_coo) *t, int m, int nnz, int *ro, int *ci, VT *va)
+{
+    FN(orc_coo_stable_sort)(t, (size_t)nnz);
+    int prev = -1;
+    for (int z = 0; z < nnz; ++z) {
+        int r = t[z].row;
+        for (int q = prev + 1; q <= r; ++q) ro[q] = z;
+        prev = r;
+        ci[z] = t[z].col;
+        va[z] = t[z].val;
+    }
+    for (int q = prev + 1; q <= m; ++q) ro[q] = nnz;
+}
+
+/* Generators: each returns CSR through caller buffers sized by the
+   matching orc_gen_*_shape().  diag/offd let the caller apply the Poisson
+   fill described in SURVEY.md Appendix B (value chosen per tuple BEFORE
+   the sort); diag == offd == 1.0 reproduces the reference default. */
+
+/* InitGrid2d -- sparse_matrix.h:458-527 (neighbour order W,E,N,S,self) */
+void FN(orc_gen_grid2d)(int w, int self_loop, VT diag, VT offd, int *ro, int *ci, VT *va)
+{
+    int m, n, nnz;
+    orc_gen_grid2d_shape(w, self_loop, &m, &n, &nnz);
+    FN(orc_coo) *t = (FN(orc_coo) *)malloc(sizeof(*t) * (size_t)(nnz ? nnz : 1));
+    int z = 0;
+    for (int j = 0; j < w; ++j)
+        for (int k = 0; k < w; ++k) {
+            int me = j * w + k;
+            if (k - 1 >= 0) { t[z].row = me; t[z].col = j * w + (k - 1); t[z].val = offd; ++z; }
+            if (k + 1 < w)  { t[z].row = me; t[z].col = j * w + (k + 1); t[z].val = offd; ++z; }
+            if (j - 1 >= 0) { t[z].row = me; t[z].col = (j - 1) * w + k; t[z].val = offd; ++z; }
+            if (j + 1 < w)  { t[z].row = me; t[z].col = (j + 1) * w + k; t[z].val = offd; ++z; }
+            if (self_loop)  { t[z].row = me; t[z].col = me; t[z].val = diag; ++z; }
+        }
+    FN(orc_coo_to_csr)(t, m, nnz, ro, ci, va);
+    free(t);
+}
+
+/* InitGrid3d -- sparse_matrix.h:533-623 (order -k,+k,-j,+j,-i,+i,self) */
+void FN(orc_gen_grid3d)(int w, int self_loop, VT diag, VT offd, int *ro, int *ci, VT *va)
+{
+    int m, n, nnz;
+    orc_gen_grid3d_shape(w, self_loop, &m, &n, &nnz);
+    FN(orc_coo) *t = (FN(orc_coo) *)malloc(sizeof(*t) * (size_t)(nnz ? nnz : 1));
+    int z = 0, ww = w * w;
+    for (int i = 0; i < w; ++i)
+        for (int j = 0; j < w; ++j)
+            for (int k = 0; k < w; ++k) {
+                int me = i * ww + j * w + k;
+                if (k - 1 >= 0) { t[z].row = me; t[z].col = me - 1;  t[z].val = offd; ++z; }
+                if (k + 1 < w)  { t[z].row = me; t[z].col = me + 1;  t[z].val = offd; ++z; }
+                if (j - 1 >= 0) { t[z].row = me; t[z].col = me - w;  t[z].val = offd; ++z; }
+                if (j + 1 < w)  { t[z].row = me; t[z].col = me + w;  t[z].val = offd; ++z; }
+                if (i - 1 >= 0) { t[z].row = me; t[z].col = me - ww; t[z].val = offd; ++z; }
+                if (i + 1 < w)  { t[z].row = me; t[z].col = me + ww; t[z].val = offd; ++z; }
+                if (self_loop)  { t[z].row = me; t[z].col = me;      t[z].val = diag; ++z; }
+            }
+    FN(orc_coo_to_csr)(t, m, nnz, ro, ci, va);
+    free(t);
+}
+
+/* InitWheel -- sparse_matrix.h:417-450: hub row 0 -> 1..s, rim i+1 -> ((i+1)%s)+1 */
+void FN(orc_gen_wheel)(int spokes, VT value, int *ro, int *ci, VT *va)
+{
+    int m = spokes + 1, nnz = 2 * spokes;
+    FN(orc_coo) *t = (FN(orc_coo) *)malloc(sizeof(*t) * (size_t)(nnz ? nnz : 1));
+    int z = 0;
+    for (int i = 0; i < spokes; ++i) { t[z].row = 0; t[z].col = i + 1; t[z].val = value; ++z; }
+    for (int i = 0; i < spokes; ++i) {
+        t[z].row = i + 1; t[z].col = ((i + 1) % spokes) + 1; t[z].val = value; ++z;
+    }
+    FN(orc_coo_to_csr)(t, m, nnz, ro, ci, va);
+    free(t);
+}
+
+/* InitDense -- sparse_matrix.h:385-412 */
+void FN(orc_gen_dense)(int rows, int cols, VT value, int *ro, int *ci, VT *va)
+{
+    int nnz = rows * cols;
+    FN(orc_coo) *t = (FN(orc_coo) *)malloc(sizeof(*t) * (size_t)(nnz ? nnz : 1));
+    for (int r = 0; r < rows; ++r)
+        for (int c = 0; c < cols; ++c) {
+            t[r * cols + c].row = r; t[r * cols + c].col = c; t[r * cols + c].val = value;
+        }
+    FN(orc_coo_to_csr)(t, rows, nnz, ro, ci, va);
+    free(t);
+}
+
+/* RHS as the CG drivers make it: srand(seed); b[i] = rand()/RAND_MAX
+   (cpu_singlecg.cpp:88-90, cpu_multicg.cpp:164-166; glibc rand) */
+void FN(orc_rhs_rand)(unsigned seed, long long count, VT *out)
+{
+    srand(seed);
+    for (long long i = 0; i < count; ++i) out[i] = (VT)rand() / (VT)RAND_MAX;
+}
+
+/* driver threshold quirk: ||b[0:n]||_2 * tol  (cpu_singlecg.cpp:23-34) */
+VT FN(orc_driver_threshold)(const VT *b, int n, VT tol)
+{
+    VT s = 0.0;
+#pragma omp parallel for reduction(+ : s)
+    for (int i = 0; i < n; ++i) s += b[i] * b[i];
+    return (VT)sqrt((double)s) * tol;
+}
+
+#undef FN
+#undef ORC_CAT
+#undef ORC_CAT_
