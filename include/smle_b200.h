@@ -1,0 +1,165 @@
+/*
+ * include/smle_b200.h -- C ABI of the B200-native merge-path SpMV / SpMM / CG library
+ * (libsmle_b200.so, built from sparse-matrix-linear-equations_b200/csrc for sm_100a).
+ *
+ * This is the drop-in boundary for the reference's data-parallel hot path.  The reference
+ * (YuyaW-0118/Sparse-Matrix-Linear-Equations) has no FFI layer: the path sits behind C++
+ * function templates called directly by its drivers.  Each entry point below names the
+ * reference function (file:line under the reference tree) it replaces; the header-only C++
+ * adapters in sparse-matrix-linear-equations_b200/host/smle_adapters.hpp keep those
+ * functions' exact signatures on top of this ABI, and INTEGRATION.md shows the call-site
+ * change a maintainer makes.
+ *
+ * Conventions
+ *  - plain C types only; matrices are CSR triples exactly as CsrMatrix<ValueT,int> holds
+ *    them (sparse_matrix.h:648-653): int row_offsets[m+1], int column_indices[nnz],
+ *    ValueT values[nnz]; dense blocks are ROW-MAJOR n x k (merge_based.hpp:97-113).
+ *  - every function returns 0 on success and a negative smle_status on failure; the text of
+ *    the last failure on the calling thread is smle_last_error().  The library never calls
+ *    exit() (the reference does: sparse_matrix.h:186-190) and never falls back to the CPU:
+ *    without a usable CUDA device every compute entry point fails with SMLE_ERR_CUDA.
+ *  - host pointers are borrowed for the duration of the call; a handle owns device copies.
+ *  - `is_device_ptr` != 0 means the vector/block arguments already live in device memory of
+ *    the current device (no copies are made); 0 means host memory (pinned or pageable).
+ *  - one process drives one GPU (torch.distributed style); the library is not re-entrant
+ *    across host threads, like the reference (hyper_parameters.hpp globals).
+ */
+#ifndef SMLE_B200_H
+#define SMLE_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct smle_csr_s *smle_csr_t;
+
+enum smle_status {
+    SMLE_OK = 0,
+    SMLE_ERR_ARG = -1,    /* bad argument (null pointer, negative size, k < 1, ...) */
+    SMLE_ERR_CUDA = -2,   /* CUDA runtime error or no device */
+    SMLE_ERR_ALLOC = -3,  /* host or device allocation failed */
+    SMLE_ERR_RANGE = -4,  /* m + nnz does not fit the reference's 32-bit merge path */
+    SMLE_ERR_COMM = -5    /* multi-GPU peer setup failed */
+};
+
+/* SpmmKernel of work_2025/types.hpp:11-16.  All three select the one merge-path kernel on
+ * the GPU (the split strategy is a CPU threading choice); the value is accepted so that
+ * CGSolveMultiple call sites keep compiling (no_pretreatment.hpp:94-105). */
+enum smle_spmm_kernel { SMLE_SIMPLE = 0, SMLE_MERGE = 1, SMLE_NONZERO_SPLIT = 2 };
+
+/* ---- library / device --------------------------------------------------------------- */
+int smle_version(void);
+const char *smle_last_error(void);
+int smle_device_count(void);                 /* 0 when no CUDA device is usable */
+int smle_init(int device);                   /* bind this process to `device`, create the stream */
+void smle_shutdown(void);
+int smle_set_stream(void *cuda_stream);      /* run on the caller's cudaStream_t (NULL: own stream) */
+void *smle_get_stream(void);                 /* the cudaStream_t kernels are launched on */
+int smle_sync(void);                         /* cudaStreamSynchronize on that stream */
+long long smle_launch_count(void);           /* kernels launched by this library so far */
+int smle_sm_count(void);
+
+/* ---- merge-path partition -----------------------------------------------------------
+ * Replaces MergePathSearch (work_2025/spmm/merge_based.hpp:22-44; copies at
+ * cpu_spmv.cpp:213-235, cub/thread/thread_search.cuh:48-83) evaluated on the share
+ * boundaries the reference threads use (merge_based.hpp:72-82): diagonal_t =
+ * min(share*t, m+nnz), share = items_per_part > 0 ? items_per_part
+ * : ceil((m+nnz)/num_parts).  row_end_offsets = row_offsets+1 (host pointer, m entries).
+ * out_xy receives 2*(num_parts+1) ints: (rows consumed, nonzeros consumed) per boundary.
+ * The search runs ON THE GPU (one thread per boundary) and must be bit-exact. */
+int smle_merge_path_partition(const int *row_end_offsets, int m, int nnz, int num_parts,
+                              int items_per_part, int *out_xy);
+
+/* ---- CSR handle ------------------------------------------------------------------------
+ * Device-resident copy of a CsrMatrix<ValueT,int> (sparse_matrix.h:633-653).  The handle
+ * also caches the tile coordinates of the merge path (they depend on A only). */
+int smle_csr_create_f64(smle_csr_t *out, int m, int n, int nnz, const int *row_offsets,
+                        const int *column_indices, const double *values);
+int smle_csr_create_f32(smle_csr_t *out, int m, int n, int nnz, const int *row_offsets,
+                        const int *column_indices, const float *values);
+void smle_csr_destroy(smle_csr_t a);
+int smle_csr_dims(smle_csr_t a, int *m, int *n, int *nnz, int *value_bytes);
+/* tile coordinates the SpMV/SpMM kernel for `k` right-hand sides uses: out_xy gets
+ * 2*(num_tiles+1) ints (capacity in ints); either output may be NULL to query sizes. */
+int smle_csr_tile_coords(smle_csr_t a, int k, int *num_tiles, int *items_per_tile,
+                         int *out_xy, int capacity);
+
+/* ---- SpMV / SpMM -----------------------------------------------------------------------
+ * smle_spmv_*: y = A x.     Replaces OmpMergeCsrmv (cpu_spmv.cpp:360-421).
+ * smle_spmm_*: Y = A X, X n x k and Y m x k row-major.
+ *              Replaces OmpMergeCsrmm (work_2025/spmm/merge_based.hpp:49-153) and, behind
+ *              the SpmmKernel switch, OmpNonzeroSplitCsrmm / OmpCsrSpmmT
+ *              (nonzero_splitting.hpp:52-150, row_splitting.hpp:18-54). */
+int smle_spmv_f64(smle_csr_t a, const double *x, double *y, int is_device_ptr);
+int smle_spmv_f32(smle_csr_t a, const float *x, float *y, int is_device_ptr);
+int smle_spmm_f64(smle_csr_t a, const double *X, double *Y, int k, int is_device_ptr);
+int smle_spmm_f32(smle_csr_t a, const float *X, float *Y, int k, int is_device_ptr);
+
+/* ---- conjugate gradient ------------------------------------------------------------------
+ * smle_cg_single_f64 replaces CGSolveSingle (work_2025/main/single_strategy.hpp:105-170):
+ *   x0 = 0, r = p = b; stop when sqrt(r.r)/||b|| < tol, tested before the p update;
+ *   *iters_out counts SpMV applications (== max_iters when not converged); ||b|| == 0 -> 1.
+ * smle_cg_multi_f64 replaces CGSolveMultiple (work_2025/main/no_pretreatment.hpp:35-197):
+ *   k lock-step recurrences over row-major n x k blocks, per-column convergence latch
+ *   (alpha = beta = 0 afterwards), stops when every column has latched.
+ *   max_err_hist (nullable, hist_capacity doubles) receives the per-iteration maximum
+ *   relative residual the reference pushes into `max_errors` (:133-155); *hist_len (nullable)
+ *   the number of iterations recorded.  `kernel` is an smle_spmm_kernel (see above).
+ * final_rel_res (nullable): sqrt(r.r)/||b|| at exit (max over columns for multi). */
+int smle_cg_single_f64(smle_csr_t a, const double *b, double *x, int max_iters, double tol,
+                       int is_device_ptr, int *iters_out, double *final_rel_res);
+int smle_cg_multi_f64(smle_csr_t a, const double *B, double *X, int k, int max_iters,
+                      double tol, int kernel, int is_device_ptr, int *iters_out,
+                      double *max_err_hist, int hist_capacity, int *hist_len,
+                      double *final_rel_res);
+
+/* Fixed-count variant for measurement: exactly `iters` CG iterations (no convergence exit),
+ * device pointers only.  Same kernels and graph as smle_cg_multi_f64. */
+int smle_cg_run_fixed_f64(smle_csr_t a, const double *B, double *X, int k, int iters);
+
+/* ---- matrix / RHS generators (host side) -------------------------------------------------
+ * CSR output identical to the reference generator followed by CsrMatrix::Init
+ * (sparse_matrix.h:668-733): InitGrid2d :458-527, InitGrid3d :533-623, InitWheel :417-450,
+ * InitDense :385-412.  `diag`/`offd` are the tuple values for row==col / row!=col
+ * (1.0/1.0 = reference default; 4/-1 and 6/-1 = the Poisson fill of SURVEY.md App. B).
+ * Caller allocates row_offsets[m+1], column_indices[nnz], values[nnz] from *_shape. */
+int smle_gen_grid2d_shape(int width, int self_loop, int *m, int *n, int *nnz);
+int smle_gen_grid3d_shape(int width, int self_loop, int *m, int *n, int *nnz);
+int smle_gen_wheel_shape(int spokes, int *m, int *n, int *nnz);
+int smle_gen_dense_shape(int rows, int cols, int *m, int *n, int *nnz);
+int smle_gen_rmat_shape(int scale, int edge_factor, int *m, int *n, int *nnz);
+int smle_gen_grid2d_f64(int width, int self_loop, double diag, double offd, int *row_offsets,
+                        int *column_indices, double *values);
+int smle_gen_grid2d_f32(int width, int self_loop, float diag, float offd, int *row_offsets,
+                        int *column_indices, float *values);
+int smle_gen_grid3d_f64(int width, int self_loop, double diag, double offd, int *row_offsets,
+                        int *column_indices, double *values);
+int smle_gen_grid3d_f32(int width, int self_loop, float diag, float offd, int *row_offsets,
+                        int *column_indices, float *values);
+int smle_gen_wheel_f64(int spokes, double value, int *row_offsets, int *column_indices,
+                       double *values);
+int smle_gen_wheel_f32(int spokes, float value, int *row_offsets, int *column_indices,
+                       float *values);
+int smle_gen_dense_f64(int rows, int cols, double value, int *row_offsets, int *column_indices,
+                       double *values);
+int smle_gen_dense_f32(int rows, int cols, float value, int *row_offsets, int *column_indices,
+                       float *values);
+/* R-MAT stand-in for the SuiteSparse set (get_uf_datasets.sh needs a network): 2^scale rows,
+ * edge_factor*2^scale edges, quadrant probabilities a,b,c,(1-a-b-c), duplicates kept, sorted
+ * by (row, col) like CsrMatrix::Init; values uniform in (0,1] or all 1.0 (unit_values). */
+int smle_gen_rmat_f64(int scale, int edge_factor, double a, double b, double c,
+                      unsigned long long seed, int unit_values, int *row_offsets,
+                      int *column_indices, double *values);
+int smle_gen_rmat_f32(int scale, int edge_factor, double a, double b, double c,
+                      unsigned long long seed, int unit_values, int *row_offsets,
+                      int *column_indices, float *values);
+/* RHS as the CG drivers build it: srand(seed); b[i] = rand()/RAND_MAX, i < count
+ * (cpu_singlecg.cpp:88-90, cpu_multicg.cpp:164-166); glibc rand(). */
+int smle_gen_rhs_rand_f64(unsigned seed, long long count, double *out);
+/* the drivers' tolerance quirk: ||b[0:n]||_2 * tol (cpu_singlecg.cpp:23-34, cpu_multicg.cpp:50-62) */
+double smle_driver_threshold_f64(const double *b, int n, double tol);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SMLE_B200_H */

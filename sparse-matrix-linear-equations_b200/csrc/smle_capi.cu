@@ -1,0 +1,679 @@
+// smle_capi.cu -- C ABI (include/smle_b200.h) over the sm_100a kernels.
+//
+// Host-side runtime of the library: device-resident CSR handles with cached merge-path tile
+// coordinates, kernel dispatch on (value type, k), the CG driver loop (CUDA-graph batches of
+// iterations with device-side convergence control), and error reporting.  No CPU fallback:
+// every compute entry point needs a CUDA device.
+#include "../../include/smle_b200.h"
+
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+
+#include <map>
+#include <new>
+#include <vector>
+
+#include "smle_cg.cuh"
+#include "smle_merge.cuh"
+
+using namespace smle;
+
+// =========================================================================================
+// error handling / globals
+// =========================================================================================
+namespace {
+
+thread_local char g_err[512] = "";
+cudaStream_t g_own_stream = nullptr;   // created by smle_init
+cudaStream_t g_stream = nullptr;       // the stream in use (own or caller's)
+int g_device = -1;
+int g_sms = 0;
+long long g_launches = 0;
+
+int fail(int code, const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CU(call)                                                                              \
+    do {                                                                                      \
+        cudaError_t e_ = (call);                                                              \
+        if (e_ != cudaSuccess)                                                                \
+            return fail(SMLE_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), \
+                        __FILE__, __LINE__);                                                  \
+    } while (0)
+
+int ensure_init()
+{
+    if (g_device >= 0) return SMLE_OK;
+    return smle_init(0);
+}
+
+int check_launch(const char *what)
+{
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(SMLE_ERR_CUDA, "launch of %s failed: %s", what, cudaGetErrorString(e));
+    return SMLE_OK;
+}
+
+} // namespace
+
+// =========================================================================================
+// CSR handle
+// =========================================================================================
+struct CgWorkspace {
+    int k = 0;
+    size_t nk = 0;
+    double *R = nullptr, *P = nullptr, *AP = nullptr;   // n x k blocks
+    double *Bd = nullptr, *Xd = nullptr;                // staging for host-pointer calls
+    double *scal = nullptr;                             // 6*k doubles + last_rel
+    int *conv = nullptr;
+    int *ctrl = nullptr;
+    double *hist = nullptr;
+    int hist_cap = 0;
+    double *part = nullptr;                             // vector-kernel partials [grid*k]
+    int *ctrl_host = nullptr;                           // pinned mirror of ctrl
+    cudaGraphExec_t graph = nullptr;                    // `graph_iters` iterations of K1,K2,K3
+    int graph_iters = 0;
+    const void *graph_B = nullptr;
+    void *graph_X = nullptr;
+    double graph_tol = 0.0;
+    bool graph_hist = false;
+};
+
+struct Partition {
+    int items_per_tile = 0;
+    int num_tiles = 0;
+    int2 *xy = nullptr;   // device, num_tiles + 1
+};
+
+struct smle_csr_s {
+    int m = 0, n = 0, nnz = 0, vbytes = 0;
+    int *ro = nullptr, *ci = nullptr;
+    void *va = nullptr;
+    std::map<int, Partition> parts;   // keyed by items per tile
+    // per-launch scratch of the merge kernel (sized for max grid)
+    int max_ctas = 0;
+    int *carry_row = nullptr;
+    void *carry_val = nullptr;  int carry_k = 0;
+    void *dot_part = nullptr, *fix_part = nullptr;
+    unsigned int *ticket = nullptr;
+    CgWorkspace ws;
+};
+
+namespace {
+
+void free_workspace(CgWorkspace &w)
+{
+    if (w.graph) cudaGraphExecDestroy(w.graph);
+    cudaFree(w.R); cudaFree(w.P); cudaFree(w.AP); cudaFree(w.Bd); cudaFree(w.Xd);
+    cudaFree(w.scal); cudaFree(w.conv); cudaFree(w.ctrl); cudaFree(w.hist); cudaFree(w.part);
+    if (w.ctrl_host) cudaFreeHost(w.ctrl_host);
+    w = CgWorkspace();
+}
+
+// ---- merge-path tiling --------------------------------------------------------------------
+constexpr int kTileItems = 2048;   // merge items per tile = workers * items-per-worker
+
+int get_partition(smle_csr_t a, int items_per_tile, Partition **out)
+{
+    auto it = a->parts.find(items_per_tile);
+    if (it != a->parts.end()) { *out = &it->second; return SMLE_OK; }
+    Partition p;
+    p.items_per_tile = items_per_tile;
+    long long total = (long long)a->m + a->nnz;
+    p.num_tiles = (int)((total + items_per_tile - 1) / items_per_tile);
+    if (p.num_tiles < 1) p.num_tiles = 1;
+    CU(cudaMalloc(&p.xy, sizeof(int2) * (size_t)(p.num_tiles + 1)));
+    int blocks = (p.num_tiles + 1 + 127) / 128;
+    merge_partition_kernel<<<blocks, 128, 0, g_stream>>>(a->ro + 1, a->m, a->nnz, items_per_tile,
+                                                         p.num_tiles, p.xy);
+    ++g_launches;
+    int rc = check_launch("merge_partition_kernel");
+    if (rc) return rc;
+    a->parts[items_per_tile] = p;
+    *out = &a->parts[items_per_tile];
+    return SMLE_OK;
+}
+
+int ensure_scratch(smle_csr_t a, int k)
+{
+    if (!a->carry_row) {
+        a->max_ctas = g_sms * 8;
+        CU(cudaMalloc(&a->carry_row, sizeof(int) * (size_t)a->max_ctas));
+        CU(cudaMalloc(&a->ticket, sizeof(unsigned int) * 4));
+        CU(cudaMemsetAsync(a->ticket, 0, sizeof(unsigned int) * 4, g_stream));
+    }
+    if (k > a->carry_k) {
+        cudaFree(a->carry_val); cudaFree(a->dot_part); cudaFree(a->fix_part);
+        a->carry_val = a->dot_part = a->fix_part = nullptr;
+        size_t bytes = (size_t)a->max_ctas * (size_t)k * 8;
+        CU(cudaMalloc(&a->carry_val, bytes));
+        CU(cudaMalloc(&a->dot_part, bytes));
+        CU(cudaMalloc(&a->fix_part, bytes));
+        a->carry_k = k;
+    }
+    return SMLE_OK;
+}
+
+// ---- kernel dispatch ------------------------------------------------------------------------
+// (G, VEC) selection: VEC = widest vector that divides k (rows of the dense block must stay
+// VEC-aligned), G = lanes needed to cover min(k, 32*VEC) columns, rounded up to a power of two.
+template <typename V>
+void pick_shape(int k, int *G, int *VEC)
+{
+    int maxvec = 16 / (int)sizeof(V);
+    int vec = 1;
+    for (int v = maxvec; v > 1; v >>= 1)
+        if (k % v == 0) { vec = v; break; }
+    int lanes = (k + vec - 1) / vec;
+    int g = 1;
+    while (g < lanes && g < 32) g <<= 1;
+    *G = g; *VEC = vec;
+}
+
+template <typename V, int G, int VEC, bool DOT>
+int launch_merge_t(smle_csr_t a, const V *X, V *Y, int k, const CgScalars &cg, bool dry)
+{
+    constexpr int IPW = kTileItems * G / kThreads;
+    constexpr int U = (VEC * sizeof(V) >= 16) ? 4 : 8;
+    Partition *p;
+    int rc = get_partition(a, kTileItems, &p);
+    if (rc) return rc;
+    rc = ensure_scratch(a, k);
+    if (rc) return rc;
+
+    static int occ = 0;   // per instantiation
+    if (!occ) {
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, merge_kernel<V, G, VEC, IPW, U, DOT>,
+                                                         kThreads, 0));
+        if (occ < 1) occ = 1;
+        if (occ > 8) occ = 8;
+    }
+    if (dry) return SMLE_OK;   // only the lazy setup (partition, scratch, occupancy) was wanted
+    const int KB = G * VEC;
+    const int col_blocks = (k + KB - 1) / KB;
+    int max_ctas = g_sms * occ;
+    if (max_ctas > a->max_ctas) max_ctas = a->max_ctas;
+    int grid = p->num_tiles < max_ctas ? p->num_tiles : max_ctas;
+    int tiles_per_cta = (p->num_tiles + grid - 1) / grid;
+    grid = (p->num_tiles + tiles_per_cta - 1) / tiles_per_cta;
+
+    MergeArgs<V> args;
+    args.row_end = a->ro + 1;
+    args.ci = a->ci;
+    args.va = (const V *)a->va;
+    args.X = X;
+    args.Y = Y;
+    args.tile_xy = p->xy;
+    args.m = a->m; args.nnz = a->nnz; args.k = k;
+    args.num_tiles = p->num_tiles; args.tiles_per_cta = tiles_per_cta;
+    args.carry_row = a->carry_row;
+    args.carry_val = (V *)a->carry_val;
+    args.dot_part = (V *)a->dot_part;
+    args.fix_part = (V *)a->fix_part;
+    args.ticket = a->ticket;
+    merge_kernel<V, G, VEC, IPW, U, DOT><<<dim3(grid, col_blocks), kThreads, 0, g_stream>>>(args, cg);
+    ++g_launches;
+    return check_launch("merge_kernel");
+}
+
+template <typename V, bool DOT>
+int launch_merge(smle_csr_t a, const V *X, V *Y, int k, const CgScalars &cg, bool dry = false)
+{
+    int G, VEC;
+    pick_shape<V>(k, &G, &VEC);
+#define SMLE_CASE(g, v) \
+    if (G == g && VEC == v) return launch_merge_t<V, g, v, DOT>(a, X, Y, k, cg, dry);
+    if constexpr (sizeof(V) == 8) {
+        SMLE_CASE(1, 1) SMLE_CASE(2, 1) SMLE_CASE(4, 1) SMLE_CASE(8, 1) SMLE_CASE(16, 1) SMLE_CASE(32, 1)
+        SMLE_CASE(1, 2) SMLE_CASE(2, 2) SMLE_CASE(4, 2) SMLE_CASE(8, 2) SMLE_CASE(16, 2) SMLE_CASE(32, 2)
+    } else {
+        SMLE_CASE(1, 1) SMLE_CASE(2, 1) SMLE_CASE(4, 1) SMLE_CASE(8, 1) SMLE_CASE(16, 1) SMLE_CASE(32, 1)
+        SMLE_CASE(1, 2) SMLE_CASE(2, 2) SMLE_CASE(4, 2) SMLE_CASE(8, 2) SMLE_CASE(16, 2) SMLE_CASE(32, 2)
+        SMLE_CASE(1, 4) SMLE_CASE(2, 4) SMLE_CASE(4, 4) SMLE_CASE(8, 4) SMLE_CASE(16, 4) SMLE_CASE(32, 4)
+    }
+#undef SMLE_CASE
+    return fail(SMLE_ERR_ARG, "no kernel for k=%d", k);
+}
+
+template <typename V>
+int csr_create(smle_csr_t *out, int m, int n, int nnz, const int *ro, const int *ci, const V *va)
+{
+    if (!out || m < 0 || n < 0 || nnz < 0 || !ro || (nnz > 0 && (!ci || !va)))
+        return fail(SMLE_ERR_ARG, "smle_csr_create: bad argument");
+    if ((long long)m + (long long)nnz > (long long)INT_MAX - kTileItems)
+        return fail(SMLE_ERR_RANGE, "m + nnz = %lld exceeds the 32-bit merge path of the reference",
+                    (long long)m + nnz);
+    int rc = ensure_init();
+    if (rc) return rc;
+    smle_csr_s *a = new (std::nothrow) smle_csr_s();
+    if (!a) return fail(SMLE_ERR_ALLOC, "out of host memory");
+    a->m = m; a->n = n; a->nnz = nnz; a->vbytes = (int)sizeof(V);
+    // 16 B of slack behind every array: tiles are staged with vector / bulk copies
+    cudaError_t e;
+    if ((e = cudaMalloc(&a->ro, sizeof(int) * ((size_t)m + 1) + 16)) != cudaSuccess ||
+        (e = cudaMalloc(&a->ci, sizeof(int) * (size_t)nnz + 16)) != cudaSuccess ||
+        (e = cudaMalloc(&a->va, sizeof(V) * (size_t)nnz + 16)) != cudaSuccess) {
+        smle_csr_destroy(a);
+        return fail(SMLE_ERR_ALLOC, "device allocation failed: %s", cudaGetErrorString(e));
+    }
+    if ((e = cudaMemcpyAsync(a->ro, ro, sizeof(int) * ((size_t)m + 1), cudaMemcpyHostToDevice, g_stream)) != cudaSuccess ||
+        (e = cudaMemcpyAsync(a->ci, ci, sizeof(int) * (size_t)nnz, cudaMemcpyHostToDevice, g_stream)) != cudaSuccess ||
+        (e = cudaMemcpyAsync(a->va, va, sizeof(V) * (size_t)nnz, cudaMemcpyHostToDevice, g_stream)) != cudaSuccess ||
+        (e = cudaStreamSynchronize(g_stream)) != cudaSuccess) {
+        smle_csr_destroy(a);
+        return fail(SMLE_ERR_CUDA, "upload failed: %s", cudaGetErrorString(e));
+    }
+    *out = a;
+    return SMLE_OK;
+}
+
+template <typename V>
+int spmm(smle_csr_t a, const V *X, V *Y, int k, int is_device_ptr)
+{
+    if (!a || !X || !Y || k < 1) return fail(SMLE_ERR_ARG, "smle_spmm: bad argument");
+    if (a->vbytes != (int)sizeof(V)) return fail(SMLE_ERR_ARG, "value type of handle does not match call");
+    int rc = ensure_init();
+    if (rc) return rc;
+    CgScalars none = {};
+    if (is_device_ptr) return launch_merge<V, false>(a, X, Y, k, none);
+    V *dX = nullptr, *dY = nullptr;
+    size_t xb = sizeof(V) * (size_t)a->n * k, yb = sizeof(V) * (size_t)a->m * k;
+    CU(cudaMalloc(&dX, xb ? xb : 16));
+    cudaError_t e = cudaMalloc(&dY, yb ? yb : 16);
+    if (e != cudaSuccess) { cudaFree(dX); return fail(SMLE_ERR_ALLOC, "device allocation failed"); }
+    rc = SMLE_OK;
+    if ((e = cudaMemcpyAsync(dX, X, xb, cudaMemcpyHostToDevice, g_stream)) != cudaSuccess)
+        rc = fail(SMLE_ERR_CUDA, "H2D failed: %s", cudaGetErrorString(e));
+    if (!rc) rc = launch_merge<V, false>(a, dX, dY, k, none);
+    if (!rc && (e = cudaMemcpyAsync(Y, dY, yb, cudaMemcpyDeviceToHost, g_stream)) != cudaSuccess)
+        rc = fail(SMLE_ERR_CUDA, "D2H failed: %s", cudaGetErrorString(e));
+    if ((e = cudaStreamSynchronize(g_stream)) != cudaSuccess && !rc)
+        rc = fail(SMLE_ERR_CUDA, "sync failed: %s", cudaGetErrorString(e));
+    cudaFree(dX); cudaFree(dY);
+    return rc;
+}
+
+// ---- CG ---------------------------------------------------------------------------------------
+constexpr int kGraphIters = 16;   // CG iterations per CUDA-graph launch
+
+int ensure_workspace(smle_csr_t a, int k, int hist_cap)
+{
+    CgWorkspace &w = a->ws;
+    if (w.k != k) {
+        free_workspace(w);
+        w.k = k;
+        w.nk = (size_t)a->m * (size_t)k;
+        size_t vb = sizeof(double) * (w.nk ? w.nk : 1);
+        CU(cudaMalloc(&w.R, vb));
+        CU(cudaMalloc(&w.P, vb));
+        CU(cudaMalloc(&w.AP, vb));
+        CU(cudaMalloc(&w.scal, sizeof(double) * (6 * (size_t)k + 1)));
+        CU(cudaMalloc(&w.conv, sizeof(int) * (size_t)k));
+        CU(cudaMalloc(&w.ctrl, sizeof(int) * CTRL_WORDS));
+        CU(cudaMalloc(&w.part, sizeof(double) * (size_t)g_sms * 8 * (size_t)k));
+        CU(cudaMallocHost(&w.ctrl_host, sizeof(int) * CTRL_WORDS * 2));
+    }
+    if (hist_cap > w.hist_cap) {
+        cudaFree(w.hist);
+        w.hist = nullptr;
+        CU(cudaMalloc(&w.hist, sizeof(double) * (size_t)hist_cap));
+        w.hist_cap = hist_cap;
+        if (w.graph) { cudaGraphExecDestroy(w.graph); w.graph = nullptr; }
+    }
+    return SMLE_OK;
+}
+
+CgScalars make_scalars(CgWorkspace &w, int k, double tol, bool want_hist)
+{
+    CgScalars s;
+    s.rs_old = w.scal;
+    s.rs_new = w.scal + k;
+    s.pAp = w.scal + 2 * (size_t)k;
+    s.alpha = w.scal + 3 * (size_t)k;
+    s.beta = w.scal + 4 * (size_t)k;
+    s.bnorm = w.scal + 5 * (size_t)k;
+    s.last_rel = w.scal + 6 * (size_t)k;
+    s.conv = w.conv;
+    s.ctrl = w.ctrl;
+    s.hist = want_hist ? w.hist : nullptr;
+    s.hist_cap = want_hist ? w.hist_cap : 0;
+    s.tol = tol;
+    return s;
+}
+
+template <int G, int VEC>
+int launch_vec_t(int which, const CgVecArgs &va, const CgScalars &cg, int max_iters, int grid)
+{
+    if (which == 0) cg_init_kernel<G, VEC><<<grid, kThreads, 0, g_stream>>>(va, cg, max_iters);
+    else if (which == 1) cg_update_r_kernel<G, VEC><<<grid, kThreads, 0, g_stream>>>(va, cg);
+    else cg_update_xp_kernel<G, VEC><<<grid, kThreads, 0, g_stream>>>(va, cg);
+    ++g_launches;
+    return check_launch("cg vector kernel");
+}
+
+int launch_vec(int which, const CgVecArgs &va, const CgScalars &cg, int max_iters)
+{
+    int G, VEC;
+    pick_shape<double>(va.k, &G, &VEC);
+    const int W = kThreads / G;
+    long long want = ((long long)va.n + W - 1) / W;
+    int grid = (int)(want < (long long)g_sms * 8 ? want : (long long)g_sms * 8);
+    if (grid < 1) grid = 1;
+#define SMLE_CASE(g, v) if (G == g && VEC == v) return launch_vec_t<g, v>(which, va, cg, max_iters, grid);
+    SMLE_CASE(1, 1) SMLE_CASE(2, 1) SMLE_CASE(4, 1) SMLE_CASE(8, 1) SMLE_CASE(16, 1) SMLE_CASE(32, 1)
+    SMLE_CASE(1, 2) SMLE_CASE(2, 2) SMLE_CASE(4, 2) SMLE_CASE(8, 2) SMLE_CASE(16, 2) SMLE_CASE(32, 2)
+#undef SMLE_CASE
+    return fail(SMLE_ERR_ARG, "no vector kernel for k=%d", va.k);
+}
+
+int launch_iteration(smle_csr_t a, const CgVecArgs &va, const CgScalars &cg)
+{
+    int rc = launch_merge<double, true>(a, va.P, va.AP, va.k, cg);
+    if (!rc) rc = launch_vec(1, va, cg, 0);
+    if (!rc) rc = launch_vec(2, va, cg, 0);
+    return rc;
+}
+
+// Solve with device pointers B, X.  tol < 0 never converges (fixed-count runs).
+int cg_solve_device(smle_csr_t a, const double *B, double *X, int k, int max_iters, double tol,
+                    int *iters_out, double *hist_out, int hist_capacity, int *hist_len,
+                    double *final_rel)
+{
+    const bool want_hist = hist_out != nullptr && hist_capacity > 0;
+    int rc = ensure_workspace(a, k, want_hist ? (max_iters < hist_capacity ? max_iters : hist_capacity) : 0);
+    if (rc) return rc;
+    rc = ensure_scratch(a, k);
+    if (rc) return rc;
+    CgWorkspace &w = a->ws;
+    CgScalars cg = make_scalars(w, k, tol, want_hist);
+    CgVecArgs va;
+    va.B = B; va.X = X; va.R = w.R; va.P = w.P; va.AP = w.AP;
+    va.n = a->m; va.k = k; va.part = w.part; va.ticket = a->ticket + 1;
+
+    rc = launch_vec(0, va, cg, max_iters);
+    if (rc) return rc;
+
+    const bool use_graph = getenv("SMLE_NO_GRAPH") == nullptr;
+    if (use_graph && (!w.graph || w.graph_B != B || w.graph_X != X || w.graph_tol != tol ||
+                      w.graph_hist != want_hist)) {
+        if (w.graph) { cudaGraphExecDestroy(w.graph); w.graph = nullptr; }
+        // lazy setup (partition kernel, occupancy query) must happen outside the capture
+        rc = launch_merge<double, true>(a, va.P, va.AP, k, cg, /*dry=*/true);
+        if (rc) return rc;
+        cudaGraph_t graph;
+        CU(cudaStreamBeginCapture(g_stream, cudaStreamCaptureModeThreadLocal));
+        for (int i = 0; i < kGraphIters && !rc; ++i) rc = launch_iteration(a, va, cg);
+        cudaError_t e = cudaStreamEndCapture(g_stream, &graph);
+        g_launches -= 3LL * kGraphIters;   // recorded, not launched
+        if (rc) return rc;
+        if (e != cudaSuccess) return fail(SMLE_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(e));
+        e = cudaGraphInstantiate(&w.graph, graph, 0);
+        cudaGraphDestroy(graph);
+        if (e != cudaSuccess) return fail(SMLE_ERR_CUDA, "graph instantiate failed: %s", cudaGetErrorString(e));
+        w.graph_iters = kGraphIters;
+        w.graph_B = B; w.graph_X = X; w.graph_tol = tol; w.graph_hist = want_hist;
+    }
+
+    // Batches of iterations.  Batch j+1 is queued before the control words of batch j are
+    // inspected, so the GPU never idles on the host round trip; after the stop flag is up the
+    // queued kernels are no-ops.
+    const int batch = use_graph ? w.graph_iters : 4;
+    cudaEvent_t ev[2];
+    CU(cudaEventCreateWithFlags(&ev[0], cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&ev[1], cudaEventDisableTiming));
+    auto submit = [&](int slot) -> int {
+        if (use_graph) {
+            CU(cudaGraphLaunch(w.graph, g_stream));
+            g_launches += 3LL * batch;
+        } else {
+            for (int i = 0; i < batch; ++i) {
+                int r2 = launch_iteration(a, va, cg);
+                if (r2) return r2;
+            }
+        }
+        CU(cudaMemcpyAsync(w.ctrl_host + slot * CTRL_WORDS, w.ctrl, sizeof(int) * CTRL_WORDS,
+                           cudaMemcpyDeviceToHost, g_stream));
+        CU(cudaEventRecord(ev[slot], g_stream));
+        return SMLE_OK;
+    };
+    if (max_iters > 0) {
+        int launched = 0, j = 0;
+        rc = submit(0);
+        launched += batch;
+        while (!rc) {
+            const bool more = launched < max_iters;
+            if (more) {
+                rc = submit((j + 1) & 1);
+                launched += batch;
+                if (rc) break;
+            }
+            CU(cudaEventSynchronize(ev[j & 1]));
+            if (w.ctrl_host[(j & 1) * CTRL_WORDS + CTRL_STOP] || !more) break;
+            ++j;
+        }
+    }
+    cudaEventDestroy(ev[0]);
+    cudaEventDestroy(ev[1]);
+    if (rc) return rc;
+
+    // final state
+    double last_rel = 0.0;
+    CU(cudaMemcpyAsync(w.ctrl_host, w.ctrl, sizeof(int) * CTRL_WORDS, cudaMemcpyDeviceToHost, g_stream));
+    CU(cudaMemcpyAsync(&last_rel, cg.last_rel, sizeof(double), cudaMemcpyDeviceToHost, g_stream));
+    CU(cudaStreamSynchronize(g_stream));
+    int iters = w.ctrl_host[CTRL_ITER];
+    if (iters_out) *iters_out = iters;
+    if (final_rel) *final_rel = last_rel;
+    if (want_hist) {
+        int nh = iters < w.hist_cap ? iters : w.hist_cap;
+        if (nh > hist_capacity) nh = hist_capacity;
+        CU(cudaMemcpy(hist_out, w.hist, sizeof(double) * (size_t)nh, cudaMemcpyDeviceToHost));
+        if (hist_len) *hist_len = nh;
+    } else if (hist_len) {
+        *hist_len = 0;
+    }
+    return SMLE_OK;
+}
+
+int cg_solve(smle_csr_t a, const double *B, double *X, int k, int max_iters, double tol,
+             int is_device_ptr, int *iters_out, double *hist, int hist_capacity, int *hist_len,
+             double *final_rel)
+{
+    if (!a || !B || !X || k < 1) return fail(SMLE_ERR_ARG, "smle_cg: bad argument");
+    if (a->vbytes != 8) return fail(SMLE_ERR_ARG, "CG needs an fp64 handle (reference CG is <double,int>)");
+    if (a->m != a->n) return fail(SMLE_ERR_ARG, "CG needs a square matrix");
+    int rc = ensure_init();
+    if (rc) return rc;
+    if (is_device_ptr)
+        return cg_solve_device(a, B, X, k, max_iters, tol, iters_out, hist, hist_capacity, hist_len, final_rel);
+    rc = ensure_workspace(a, k, 0);
+    if (rc) return rc;
+    CgWorkspace &w = a->ws;
+    size_t vb = sizeof(double) * (w.nk ? w.nk : 1);
+    if (!w.Bd) { CU(cudaMalloc(&w.Bd, vb)); CU(cudaMalloc(&w.Xd, vb)); }
+    CU(cudaMemcpyAsync(w.Bd, B, sizeof(double) * w.nk, cudaMemcpyHostToDevice, g_stream));
+    rc = cg_solve_device(a, w.Bd, w.Xd, k, max_iters, tol, iters_out, hist, hist_capacity, hist_len, final_rel);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(X, w.Xd, sizeof(double) * w.nk, cudaMemcpyDeviceToHost, g_stream));
+    CU(cudaStreamSynchronize(g_stream));
+    return SMLE_OK;
+}
+
+} // namespace
+
+// =========================================================================================
+// exported C ABI
+// =========================================================================================
+extern "C" {
+
+int smle_version(void) { return 100; }
+const char *smle_last_error(void) { return g_err; }
+
+int smle_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int smle_init(int device)
+{
+    int n = smle_device_count();
+    if (n < 1) return fail(SMLE_ERR_CUDA, "no CUDA device: this library has no CPU fallback");
+    if (device < 0 || device >= n) return fail(SMLE_ERR_ARG, "device %d out of range (%d visible)", device, n);
+    CU(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    g_sms = prop.multiProcessorCount;
+    const bool using_own = (g_stream == g_own_stream);
+    if (g_own_stream) cudaStreamDestroy(g_own_stream);
+    CU(cudaStreamCreateWithFlags(&g_own_stream, cudaStreamNonBlocking));
+    g_device = device;
+    if (using_own) g_stream = g_own_stream;
+    return SMLE_OK;
+}
+
+void smle_shutdown(void)
+{
+    if (g_own_stream) cudaStreamDestroy(g_own_stream);
+    g_own_stream = g_stream = nullptr;
+    g_device = -1;
+}
+
+int smle_set_stream(void *s)
+{
+    int rc = ensure_init();
+    if (rc) return rc;
+    g_stream = s ? (cudaStream_t)s : g_own_stream;
+    return SMLE_OK;
+}
+
+void *smle_get_stream(void) { return (void *)g_stream; }
+
+int smle_sync(void)
+{
+    int rc = ensure_init();
+    if (rc) return rc;
+    CU(cudaStreamSynchronize(g_stream));
+    return SMLE_OK;
+}
+
+long long smle_launch_count(void) { return g_launches; }
+int smle_sm_count(void) { return ensure_init() ? 0 : g_sms; }
+
+int smle_merge_path_partition(const int *row_end, int m, int nnz, int num_parts, int items_per_part,
+                              int *out_xy)
+{
+    if (!row_end && m > 0) return fail(SMLE_ERR_ARG, "row_end_offsets is NULL");
+    if (m < 0 || nnz < 0 || num_parts < 1 || !out_xy) return fail(SMLE_ERR_ARG, "bad argument");
+    long long total = (long long)m + nnz;
+    if (total > INT_MAX) return fail(SMLE_ERR_RANGE, "m + nnz overflows int");
+    int rc = ensure_init();
+    if (rc) return rc;
+    int share = items_per_part > 0 ? items_per_part : (int)((total + num_parts - 1) / num_parts);
+    int *d_row_end = nullptr;
+    int2 *d_out = nullptr;
+    CU(cudaMalloc(&d_row_end, sizeof(int) * (size_t)(m > 0 ? m : 1)));
+    cudaError_t e = cudaMalloc(&d_out, sizeof(int2) * (size_t)(num_parts + 1));
+    if (e != cudaSuccess) { cudaFree(d_row_end); return fail(SMLE_ERR_ALLOC, "device allocation failed"); }
+    rc = SMLE_OK;
+    if ((e = cudaMemcpyAsync(d_row_end, row_end, sizeof(int) * (size_t)m, cudaMemcpyHostToDevice, g_stream)) != cudaSuccess)
+        rc = fail(SMLE_ERR_CUDA, "H2D failed: %s", cudaGetErrorString(e));
+    if (!rc) {
+        merge_partition_kernel<<<(num_parts + 1 + 127) / 128, 128, 0, g_stream>>>(d_row_end, m, nnz, share,
+                                                                                  num_parts, d_out);
+        ++g_launches;
+        rc = check_launch("merge_partition_kernel");
+    }
+    if (!rc && (e = cudaMemcpyAsync(out_xy, d_out, sizeof(int2) * (size_t)(num_parts + 1),
+                                    cudaMemcpyDeviceToHost, g_stream)) != cudaSuccess)
+        rc = fail(SMLE_ERR_CUDA, "D2H failed: %s", cudaGetErrorString(e));
+    if ((e = cudaStreamSynchronize(g_stream)) != cudaSuccess && !rc)
+        rc = fail(SMLE_ERR_CUDA, "sync failed: %s", cudaGetErrorString(e));
+    cudaFree(d_row_end); cudaFree(d_out);
+    return rc;
+}
+
+int smle_csr_create_f64(smle_csr_t *out, int m, int n, int nnz, const int *ro, const int *ci, const double *va)
+{
+    return csr_create<double>(out, m, n, nnz, ro, ci, va);
+}
+int smle_csr_create_f32(smle_csr_t *out, int m, int n, int nnz, const int *ro, const int *ci, const float *va)
+{
+    return csr_create<float>(out, m, n, nnz, ro, ci, va);
+}
+
+void smle_csr_destroy(smle_csr_t a)
+{
+    if (!a) return;
+    if (g_stream) cudaStreamSynchronize(g_stream);
+    free_workspace(a->ws);
+    for (auto &kv : a->parts) cudaFree(kv.second.xy);
+    cudaFree(a->ro); cudaFree(a->ci); cudaFree(a->va);
+    cudaFree(a->carry_row); cudaFree(a->carry_val); cudaFree(a->dot_part); cudaFree(a->fix_part);
+    cudaFree(a->ticket);
+    delete a;
+}
+
+int smle_csr_dims(smle_csr_t a, int *m, int *n, int *nnz, int *value_bytes)
+{
+    if (!a) return fail(SMLE_ERR_ARG, "null handle");
+    if (m) *m = a->m;
+    if (n) *n = a->n;
+    if (nnz) *nnz = a->nnz;
+    if (value_bytes) *value_bytes = a->vbytes;
+    return SMLE_OK;
+}
+
+int smle_csr_tile_coords(smle_csr_t a, int k, int *num_tiles, int *items_per_tile, int *out_xy, int capacity)
+{
+    if (!a || k < 1) return fail(SMLE_ERR_ARG, "bad argument");
+    int rc = ensure_init();
+    if (rc) return rc;
+    Partition *p;
+    rc = get_partition(a, kTileItems, &p);
+    if (rc) return rc;
+    if (num_tiles) *num_tiles = p->num_tiles;
+    if (items_per_tile) *items_per_tile = p->items_per_tile;
+    if (out_xy) {
+        if (capacity < 2 * (p->num_tiles + 1)) return fail(SMLE_ERR_ARG, "out_xy too small");
+        CU(cudaMemcpyAsync(out_xy, p->xy, sizeof(int2) * (size_t)(p->num_tiles + 1), cudaMemcpyDeviceToHost, g_stream));
+        CU(cudaStreamSynchronize(g_stream));
+    }
+    return SMLE_OK;
+}
+
+int smle_spmv_f64(smle_csr_t a, const double *x, double *y, int dev) { return spmm<double>(a, x, y, 1, dev); }
+int smle_spmv_f32(smle_csr_t a, const float *x, float *y, int dev) { return spmm<float>(a, x, y, 1, dev); }
+int smle_spmm_f64(smle_csr_t a, const double *X, double *Y, int k, int dev) { return spmm<double>(a, X, Y, k, dev); }
+int smle_spmm_f32(smle_csr_t a, const float *X, float *Y, int k, int dev) { return spmm<float>(a, X, Y, k, dev); }
+
+int smle_cg_single_f64(smle_csr_t a, const double *b, double *x, int max_iters, double tol, int dev,
+                       int *iters_out, double *final_rel_res)
+{
+    return cg_solve(a, b, x, 1, max_iters, tol, dev, iters_out, nullptr, 0, nullptr, final_rel_res);
+}
+
+int smle_cg_multi_f64(smle_csr_t a, const double *B, double *X, int k, int max_iters, double tol, int kernel,
+                      int dev, int *iters_out, double *hist, int hist_capacity, int *hist_len,
+                      double *final_rel_res)
+{
+    if (kernel < SMLE_SIMPLE || kernel > SMLE_NONZERO_SPLIT) return fail(SMLE_ERR_ARG, "unknown SpmmKernel %d", kernel);
+    return cg_solve(a, B, X, k, max_iters, tol, dev, iters_out, hist, hist_capacity, hist_len, final_rel_res);
+}
+
+int smle_cg_run_fixed_f64(smle_csr_t a, const double *B, double *X, int k, int iters)
+{
+    return cg_solve(a, B, X, k, iters, -1.0, 1, nullptr, nullptr, 0, nullptr, nullptr);
+}
+
+} // extern "C"

@@ -1,0 +1,228 @@
+// smle_cg.cuh -- fused CG vector kernels for sm_100a (fp64).
+//
+// One CG iteration of the reference (single_strategy.hpp:134-163 / no_pretreatment.hpp:90-182)
+// is SpMM + 3 dot sweeps + 2 axpy sweeps + 1 p-update sweep (+ a memset), i.e. ~14 passes over
+// the n x k blocks.  Here it is three kernels and 10 passes, with every scalar on the device:
+//
+//   K1  merge_kernel<DOT>     AP = A P, pAp partials while rows are emitted; last CTA: alpha
+//   K2  cg_update_r_kernel    R -= alpha AP, r.r partials; last CTA: rs_new, convergence
+//                             latch, beta, error history, iteration counter, stop flag
+//   K3  cg_update_xp_kernel   X += alpha P;  P = R + beta P
+//
+// The arithmetic per element is the reference's (same operations on the same operands); only
+// the sweep boundaries moved.  Per-column dot products are reduced deterministically: each CTA
+// writes one partial per column and the last CTA to finish adds them in CTA order.
+//
+// Thread mapping (shared with the SpMM kernel): a "worker" of G lanes covers KB = G*VEC
+// consecutive columns of one row with VEC-wide (up to 128-bit) accesses; workers stride over
+// rows, column blocks of KB columns are looped inside the kernel.
+#pragma once
+#include "smle_common.cuh"
+
+namespace smle {
+
+struct CgVecArgs {
+    const double *__restrict__ B;
+    double *__restrict__ X;
+    double *__restrict__ R;
+    double *__restrict__ P;
+    double *__restrict__ AP;
+    int n, k;
+    double *part;          // [gridDim.x * k] per-CTA partials
+    unsigned int *ticket;
+};
+
+// reduce VEC per-lane partials over the workers of a CTA and publish them for this CTA
+template <int G, int VEC>
+__device__ __forceinline__ void publish_partials(double (&s)[VEC], int cb, int k, double *part,
+                                                 double (*s_w)[G * VEC])
+{
+    constexpr int KB = G * VEC;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int li = tid % G, wl = lane / G;
+#pragma unroll
+    for (int d = G; d < 32; d <<= 1) {
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) s[v] += __shfl_xor_sync(0xffffffffu, s[v], d);
+    }
+    __syncthreads();
+    if (wl == 0) {
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) s_w[warp][li * VEC + v] = s[v];
+    }
+    __syncthreads();
+    if (tid < KB) {
+        double t = 0;
+        for (int i = 0; i < kWarps; ++i) t += s_w[i][tid];
+        int c = cb * KB + tid;
+        if (c < k) part[(size_t)blockIdx.x * k + c] = t;
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// cg_init_kernel: X = 0, R = P = B, b.b partials  (no_pretreatment.hpp:63-81,
+// single_strategy.hpp:120-131).  Last CTA: bnorm = sqrt(b.b) (0 -> 1), rs_old = b.b,
+// latches cleared, control words reset.
+// ---------------------------------------------------------------------------------------
+template <int G, int VEC>
+__global__ void __launch_bounds__(kThreads)
+cg_init_kernel(CgVecArgs a, CgScalars cg, int max_iters)
+{
+    constexpr int W = kThreads / G, KB = G * VEC;
+    __shared__ double s_w[kWarps][KB];
+    __shared__ double s_red[kThreads];
+    const int tid = threadIdx.x, w = tid / G, li = tid % G;
+    const size_t k = (size_t)a.k;
+
+    for (int cb = 0; cb * KB < a.k; ++cb) {
+        const int c0 = cb * KB + li * VEC;
+        double s[VEC];
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) s[v] = 0;
+        if (c0 < a.k) {
+            for (int row = blockIdx.x * W + w; row < a.n; row += gridDim.x * W) {
+                size_t off = (size_t)row * k + c0;
+                double b[VEC], z[VEC];
+                ldg_vec<double, VEC>(b, a.B + off);
+#pragma unroll
+                for (int v = 0; v < VEC; ++v) { z[v] = 0; s[v] += b[v] * b[v]; }
+                st_vec<double, VEC>(a.X + off, z);
+                st_vec<double, VEC>(a.R + off, b);
+                st_vec<double, VEC>(a.P + off, b);
+            }
+        }
+        publish_partials<G, VEC>(s, cb, a.k, a.part, s_w);
+    }
+
+    if (!last_cta_election(a.ticket, gridDim.x)) return;
+    cta_reduce_columns<double>(a.part, nullptr, gridDim.x, a.k, cg.rs_old, s_red);
+    for (int c = tid; c < a.k; c += kThreads) {
+        double nb = sqrt(cg.rs_old[c]);
+        cg.bnorm[c] = nb == 0.0 ? 1.0 : nb;
+        cg.conv[c] = 0;
+    }
+    if (tid == 0) {
+        cg.ctrl[CTRL_ITER] = 0;
+        cg.ctrl[CTRL_STOP] = max_iters <= 0 ? 1 : 0;
+        cg.ctrl[CTRL_HALT] = max_iters <= 0 ? 1 : 0;
+        cg.ctrl[CTRL_MAX_ITERS] = max_iters;
+        cg.ctrl[CTRL_NCONV] = 0;
+        *cg.last_rel = 0.0;
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// K2: R -= alpha * AP and r.r  (no_pretreatment.hpp:125-130; single_strategy.hpp:147-149).
+// Last CTA: rs_new, per-column relative residual and latch (:133-155), beta (:165-176),
+// rs_old <- rs_new (:179-181), history, iteration count, stop flag (:157-161 or max_iters).
+// ---------------------------------------------------------------------------------------
+template <int G, int VEC>
+__global__ void __launch_bounds__(kThreads)
+cg_update_r_kernel(CgVecArgs a, CgScalars cg)
+{
+    constexpr int W = kThreads / G, KB = G * VEC;
+    __shared__ double s_w[kWarps][KB];
+    __shared__ double s_red[kThreads];
+    __shared__ int s_cnt[kThreads];
+    if (cg.ctrl[CTRL_STOP]) return;
+    const int tid = threadIdx.x, w = tid / G, li = tid % G;
+    const size_t k = (size_t)a.k;
+
+    for (int cb = 0; cb * KB < a.k; ++cb) {
+        const int c0 = cb * KB + li * VEC;
+        double s[VEC];
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) s[v] = 0;
+        if (c0 < a.k) {
+            double na[VEC];
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) na[v] = -cg.alpha[c0 + v];
+            for (int row = blockIdx.x * W + w; row < a.n; row += gridDim.x * W) {
+                size_t off = (size_t)row * k + c0;
+                double r[VEC], ap[VEC];
+                ld_vec<double, VEC>(r, a.R + off);
+                ld_vec<double, VEC>(ap, a.AP + off);
+#pragma unroll
+                for (int v = 0; v < VEC; ++v) { r[v] += na[v] * ap[v]; s[v] += r[v] * r[v]; }
+                st_vec<double, VEC>(a.R + off, r);
+            }
+        }
+        publish_partials<G, VEC>(s, cb, a.k, a.part, s_w);
+    }
+
+    if (!last_cta_election(a.ticket, gridDim.x)) return;
+    cta_reduce_columns<double>(a.part, nullptr, gridDim.x, a.k, cg.rs_new, s_red);
+
+    double worst = 0.0;
+    int nconv = 0;
+    for (int c = tid; c < a.k; c += kThreads) {
+        const double rn = cg.rs_new[c], ro = cg.rs_old[c];
+        const double rel = sqrt(rn) / cg.bnorm[c];
+        worst = fmax(worst, rel);
+        int cv = cg.conv[c];
+        if (!cv && rel < cg.tol) { cv = 1; cg.conv[c] = 1; }
+        nconv += cv;
+        cg.beta[c] = cv ? 0.0 : rn / ro;
+        cg.rs_old[c] = rn;
+    }
+    s_red[tid] = worst;
+    s_cnt[tid] = nconv;
+    __syncthreads();
+    for (int d = kThreads / 2; d > 0; d >>= 1) {
+        if (tid < d) {
+            s_red[tid] = fmax(s_red[tid], s_red[tid + d]);
+            s_cnt[tid] += s_cnt[tid + d];
+        }
+        __syncthreads();
+    }
+    if (tid == 0) {
+        const int it = cg.ctrl[CTRL_ITER];
+        if (cg.hist && it < cg.hist_cap) cg.hist[it] = s_red[0];
+        *cg.last_rel = s_red[0];
+        cg.ctrl[CTRL_ITER] = it + 1;
+        cg.ctrl[CTRL_NCONV] = s_cnt[0];
+        if (s_cnt[0] == a.k || it + 1 >= cg.ctrl[CTRL_MAX_ITERS]) cg.ctrl[CTRL_STOP] = 1;
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// K3: X += alpha * P (no_pretreatment.hpp:123) and, unless this was the final iteration,
+// P = R + beta * P (:177).  HALT is raised by the first K1 that sees STOP, i.e. after the
+// final iteration's K3 has run.
+// ---------------------------------------------------------------------------------------
+template <int G, int VEC>
+__global__ void __launch_bounds__(kThreads)
+cg_update_xp_kernel(CgVecArgs a, CgScalars cg)
+{
+    constexpr int W = kThreads / G, KB = G * VEC;
+    if (cg.ctrl[CTRL_HALT]) return;
+    const bool final_iter = cg.ctrl[CTRL_STOP] != 0;
+    const int tid = threadIdx.x, w = tid / G, li = tid % G;
+    const size_t k = (size_t)a.k;
+
+    for (int cb = 0; cb * KB < a.k; ++cb) {
+        const int c0 = cb * KB + li * VEC;
+        if (c0 >= a.k) continue;
+        double al[VEC], be[VEC];
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) { al[v] = cg.alpha[c0 + v]; be[v] = cg.beta[c0 + v]; }
+        for (int row = blockIdx.x * W + w; row < a.n; row += gridDim.x * W) {
+            size_t off = (size_t)row * k + c0;
+            double x[VEC], p[VEC];
+            ld_vec<double, VEC>(x, a.X + off);
+            ld_vec<double, VEC>(p, a.P + off);
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) x[v] += al[v] * p[v];
+            st_vec<double, VEC>(a.X + off, x);
+            if (!final_iter) {
+                double r[VEC];
+                ld_vec<double, VEC>(r, a.R + off);
+#pragma unroll
+                for (int v = 0; v < VEC; ++v) p[v] = r[v] + be[v] * p[v];
+                st_vec<double, VEC>(a.P + off, p);
+            }
+        }
+    }
+}
+
+} // namespace smle

@@ -1,0 +1,161 @@
+// smle_common.cuh -- shared device helpers for the sm_100a merge-path SpMV/SpMM/CG kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <limits.h>
+#include <stdint.h>
+#include <string.h>
+
+namespace smle {
+
+constexpr int kThreads = 256;          // threads per CTA for every kernel in the library
+constexpr int kWarps = kThreads / 32;
+
+// ---------------------------------------------------------------------------------------
+// CG scalar state, device resident (all arrays have k entries).  The iteration loop never
+// reads these on the host except through one async copy of `ctrl` per graph batch.
+// ---------------------------------------------------------------------------------------
+enum CtrlSlot { CTRL_ITER = 0, CTRL_STOP = 1, CTRL_HALT = 2, CTRL_MAX_ITERS = 3, CTRL_NCONV = 4,
+                CTRL_WORDS = 8 };
+
+struct CgScalars {
+    double *rs_old;    // r.r of the previous iteration          (no_pretreatment.hpp:81,179-181)
+    double *rs_new;    // r.r of this iteration                  (:130)
+    double *pAp;       // p.Ap                                   (:107)
+    double *alpha;     // rs_old/pAp, 0 once latched             (:109-120)
+    double *beta;      // rs_new/rs_old, 0 once latched          (:165-176)
+    double *bnorm;     // ||b||, 0 replaced by 1                 (:71-79)
+    int *conv;         // per-column convergence latch           (:133-155)
+    int *ctrl;         // CtrlSlot words
+    double *hist;      // max relative residual per iteration    (:150-155), nullable
+    double *last_rel;  // max relative residual of the last iteration (1 double)
+    int hist_cap;
+    double tol;
+};
+
+// ---------------------------------------------------------------------------------------
+// vector load / store of VEC consecutive values (VEC*sizeof(V) in {4, 8, 16} bytes)
+// ---------------------------------------------------------------------------------------
+template <typename V, int VEC>
+__device__ __forceinline__ void ldg_vec(V (&out)[VEC], const V *p)
+{
+    if constexpr (sizeof(V) * VEC == 16) {
+        int4 t = __ldg(reinterpret_cast<const int4 *>(p));
+        memcpy(out, &t, 16);
+    } else if constexpr (sizeof(V) * VEC == 8) {
+        int2 t = __ldg(reinterpret_cast<const int2 *>(p));
+        memcpy(out, &t, 8);
+    } else {
+        int t = __ldg(reinterpret_cast<const int *>(p));
+        memcpy(out, &t, 4);
+    }
+}
+
+// coherent (L2) load: for data another CTA of the same launch may have written
+template <typename V, int VEC>
+__device__ __forceinline__ void ldcg_vec(V (&out)[VEC], const V *p)
+{
+    if constexpr (sizeof(V) * VEC == 16) {
+        int4 t = __ldcg(reinterpret_cast<const int4 *>(p));
+        memcpy(out, &t, 16);
+    } else if constexpr (sizeof(V) * VEC == 8) {
+        int2 t = __ldcg(reinterpret_cast<const int2 *>(p));
+        memcpy(out, &t, 8);
+    } else {
+        int t = __ldcg(reinterpret_cast<const int *>(p));
+        memcpy(out, &t, 4);
+    }
+}
+
+template <typename V, int VEC>
+__device__ __forceinline__ void ld_vec(V (&out)[VEC], const V *p)
+{
+    if constexpr (sizeof(V) * VEC == 16) {
+        int4 t = *reinterpret_cast<const int4 *>(p);
+        memcpy(out, &t, 16);
+    } else if constexpr (sizeof(V) * VEC == 8) {
+        int2 t = *reinterpret_cast<const int2 *>(p);
+        memcpy(out, &t, 8);
+    } else {
+        int t = *reinterpret_cast<const int *>(p);
+        memcpy(out, &t, 4);
+    }
+}
+
+template <typename V, int VEC>
+__device__ __forceinline__ void st_vec(V *p, const V (&in)[VEC])
+{
+    if constexpr (sizeof(V) * VEC == 16) {
+        int4 t;
+        memcpy(&t, in, 16);
+        *reinterpret_cast<int4 *>(p) = t;
+    } else if constexpr (sizeof(V) * VEC == 8) {
+        int2 t;
+        memcpy(&t, in, 8);
+        *reinterpret_cast<int2 *>(p) = t;
+    } else {
+        int t;
+        memcpy(&t, in, 4);
+        *reinterpret_cast<int *>(p) = t;
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// "last CTA done" election (threadFenceReduction pattern): every CTA publishes its global
+// writes, takes a ticket, and the CTA that draws the last ticket runs the serial epilogue
+// (carry fix-up, deterministic reduction of the per-CTA partials, CG scalars).  The ticket
+// counter is reset by the winner so the next launch starts from zero.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ bool last_cta_election(unsigned int *ticket, unsigned int num_ctas)
+{
+    __shared__ bool s_is_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned int t = atomicAdd(ticket, 1u);
+        s_is_last = (t == num_ctas - 1u);
+    }
+    __syncthreads();
+    bool last = s_is_last;
+    if (last) {
+        __threadfence();
+        if (threadIdx.x == 0) *ticket = 0u;
+    }
+    return last;
+}
+
+// ---------------------------------------------------------------------------------------
+// Deterministic column-wise reduction of per-CTA partials by ONE CTA:
+//   out[c] = sum_e (src1[e*k+c] + (src2 ? src2[e*k+c] : 0)),  e in [0, entries)
+// The order of additions is fixed by (kThreads, entries, k) only, so results are
+// reproducible run to run.  red: shared scratch of kThreads values.
+// ---------------------------------------------------------------------------------------
+template <typename V>
+__device__ __forceinline__ void cta_reduce_columns(const V *src1, const V *src2, int entries, int k,
+                                                   V *out, V *red)
+{
+    const int tid = threadIdx.x;
+    for (int cbase = 0; cbase < k; cbase += kThreads) {
+        const int kk = min(k - cbase, kThreads);       // columns in this pass
+        const int parts = kThreads / kk;               // threads cooperating per column
+        const int c = tid % kk, part = tid / kk;
+        V s = 0;
+        if (part < parts) {
+            for (int e = part; e < entries; e += parts) {
+                size_t o = (size_t)e * k + cbase + c;
+                s += __ldcg(src1 + o);
+                if (src2) s += __ldcg(src2 + o);
+            }
+        }
+        __syncthreads();
+        red[tid] = s;
+        __syncthreads();
+        if (tid < kk) {
+            V t = 0;
+            for (int p = 0; p < parts; ++p) t += red[p * kk + tid];
+            out[cbase + tid] = t;
+        }
+    }
+    __syncthreads();
+}
+
+} // namespace smle
