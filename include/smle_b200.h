@@ -116,6 +116,11 @@ int smle_cg_multi_f64(smle_csr_t a, const double *B, double *X, int k, int max_i
 /* Fixed-count variant for measurement: exactly `iters` CG iterations (no convergence exit),
  * device pointers only.  Same kernels and graph as smle_cg_multi_f64. */
 int smle_cg_run_fixed_f64(smle_csr_t a, const double *B, double *X, int k, int iters);
+/* Per-kernel timing for the roofline report: runs `iters` CG iterations WITHOUT the CUDA graph,
+ * bracketing each of the three kernels of an iteration with CUDA events on the launch stream.
+ * ms_per_kernel[3] = mean milliseconds of {SpMM+dot, r-update+dot, x/p-update}. Device pointers. */
+int smle_cg_profile_f64(smle_csr_t a, const double *B, double *X, int k, int iters,
+                        float *ms_per_kernel);
 
 /* ---- matrix / RHS generators (host side) -------------------------------------------------
  * CSR output identical to the reference generator followed by CsrMatrix::Init

@@ -72,8 +72,9 @@ struct CgWorkspace {
     int k = 0;
     size_t nk = 0;
     double *R = nullptr, *P = nullptr, *AP = nullptr;   // n x k blocks
-    double *Bd = nullptr, *Xd = nullptr;                // staging for host-pointer calls
-    double *scal = nullptr;                             // 6*k doubles + last_rel
+    double *Bd = nullptr;                               // staging of B for host-pointer calls
+    double *Xd = nullptr;                               // the iterate (graphs bake this pointer)
+    double *scal = nullptr;                             // 6*k doubles + last_rel + tol
     int *conv = nullptr;
     int *ctrl = nullptr;
     double *hist = nullptr;
@@ -82,10 +83,6 @@ struct CgWorkspace {
     int *ctrl_host = nullptr;                           // pinned mirror of ctrl
     cudaGraphExec_t graph = nullptr;                    // `graph_iters` iterations of K1,K2,K3
     int graph_iters = 0;
-    const void *graph_B = nullptr;
-    void *graph_X = nullptr;
-    double graph_tol = 0.0;
-    bool graph_hist = false;
 };
 
 struct Partition {
@@ -316,12 +313,14 @@ int ensure_workspace(smle_csr_t a, int k, int hist_cap)
         CU(cudaMalloc(&w.R, vb));
         CU(cudaMalloc(&w.P, vb));
         CU(cudaMalloc(&w.AP, vb));
-        CU(cudaMalloc(&w.scal, sizeof(double) * (6 * (size_t)k + 1)));
+        CU(cudaMalloc(&w.scal, sizeof(double) * (6 * (size_t)k + 2)));
+        CU(cudaMalloc(&w.Xd, vb));
         CU(cudaMalloc(&w.conv, sizeof(int) * (size_t)k));
         CU(cudaMalloc(&w.ctrl, sizeof(int) * CTRL_WORDS));
         CU(cudaMalloc(&w.part, sizeof(double) * (size_t)g_sms * 8 * (size_t)k));
-        CU(cudaMallocHost(&w.ctrl_host, sizeof(int) * CTRL_WORDS * 2));
+        CU(cudaMallocHost(&w.ctrl_host, sizeof(int) * CTRL_WORDS * 4));
     }
+    if (hist_cap < 1) hist_cap = 1;
     if (hist_cap > w.hist_cap) {
         cudaFree(w.hist);
         w.hist = nullptr;
@@ -332,7 +331,7 @@ int ensure_workspace(smle_csr_t a, int k, int hist_cap)
     return SMLE_OK;
 }
 
-CgScalars make_scalars(CgWorkspace &w, int k, double tol, bool want_hist)
+CgScalars make_scalars(CgWorkspace &w, int k)
 {
     CgScalars s;
     s.rs_old = w.scal;
@@ -344,23 +343,23 @@ CgScalars make_scalars(CgWorkspace &w, int k, double tol, bool want_hist)
     s.last_rel = w.scal + 6 * (size_t)k;
     s.conv = w.conv;
     s.ctrl = w.ctrl;
-    s.hist = want_hist ? w.hist : nullptr;
-    s.hist_cap = want_hist ? w.hist_cap : 0;
-    s.tol = tol;
+    s.tol = w.scal + 6 * (size_t)k + 1;
+    s.hist = w.hist;
+    s.hist_cap = w.hist_cap;
     return s;
 }
 
 template <int G, int VEC>
-int launch_vec_t(int which, const CgVecArgs &va, const CgScalars &cg, int max_iters, int grid)
+int launch_vec_t(int which, const CgVecArgs &va, const CgScalars &cg, int max_iters, double tol, int grid)
 {
-    if (which == 0) cg_init_kernel<G, VEC><<<grid, kThreads, 0, g_stream>>>(va, cg, max_iters);
+    if (which == 0) cg_init_kernel<G, VEC><<<grid, kThreads, 0, g_stream>>>(va, cg, max_iters, tol);
     else if (which == 1) cg_update_r_kernel<G, VEC><<<grid, kThreads, 0, g_stream>>>(va, cg);
     else cg_update_xp_kernel<G, VEC><<<grid, kThreads, 0, g_stream>>>(va, cg);
     ++g_launches;
     return check_launch("cg vector kernel");
 }
 
-int launch_vec(int which, const CgVecArgs &va, const CgScalars &cg, int max_iters)
+int launch_vec(int which, const CgVecArgs &va, const CgScalars &cg, int max_iters = 0, double tol = 0.0)
 {
     int G, VEC;
     pick_shape<double>(va.k, &G, &VEC);
@@ -368,7 +367,7 @@ int launch_vec(int which, const CgVecArgs &va, const CgScalars &cg, int max_iter
     long long want = ((long long)va.n + W - 1) / W;
     int grid = (int)(want < (long long)g_sms * 8 ? want : (long long)g_sms * 8);
     if (grid < 1) grid = 1;
-#define SMLE_CASE(g, v) if (G == g && VEC == v) return launch_vec_t<g, v>(which, va, cg, max_iters, grid);
+#define SMLE_CASE(g, v) if (G == g && VEC == v) return launch_vec_t<g, v>(which, va, cg, max_iters, tol, grid);
     SMLE_CASE(1, 1) SMLE_CASE(2, 1) SMLE_CASE(4, 1) SMLE_CASE(8, 1) SMLE_CASE(16, 1) SMLE_CASE(32, 1)
     SMLE_CASE(1, 2) SMLE_CASE(2, 2) SMLE_CASE(4, 2) SMLE_CASE(8, 2) SMLE_CASE(16, 2) SMLE_CASE(32, 2)
 #undef SMLE_CASE
@@ -378,14 +377,16 @@ int launch_vec(int which, const CgVecArgs &va, const CgScalars &cg, int max_iter
 int launch_iteration(smle_csr_t a, const CgVecArgs &va, const CgScalars &cg)
 {
     int rc = launch_merge<double, true>(a, va.P, va.AP, va.k, cg);
-    if (!rc) rc = launch_vec(1, va, cg, 0);
-    if (!rc) rc = launch_vec(2, va, cg, 0);
+    if (!rc) rc = launch_vec(1, va, cg);
+    if (!rc) rc = launch_vec(2, va, cg);
     return rc;
 }
 
-// Solve with device pointers B, X.  tol < 0 never converges (fixed-count runs).
-int cg_solve_device(smle_csr_t a, const double *B, double *X, int k, int max_iters, double tol,
-                    int *iters_out, double *hist_out, int hist_capacity, int *hist_len,
+// Solve A X = B.  B is a device pointer; the iterate lives in the workspace (w.Xd) so that the
+// captured graph never depends on caller pointers; the result is copied to X_dev (device) or
+// X_host (host) at the end.  tol < 0 never converges (fixed-count runs).
+int cg_solve_device(smle_csr_t a, const double *B, double *X_dev, double *X_host, int k, int max_iters,
+                    double tol, int *iters_out, double *hist_out, int hist_capacity, int *hist_len,
                     double *final_rel)
 {
     const bool want_hist = hist_out != nullptr && hist_capacity > 0;
@@ -394,18 +395,16 @@ int cg_solve_device(smle_csr_t a, const double *B, double *X, int k, int max_ite
     rc = ensure_scratch(a, k);
     if (rc) return rc;
     CgWorkspace &w = a->ws;
-    CgScalars cg = make_scalars(w, k, tol, want_hist);
+    CgScalars cg = make_scalars(w, k);
     CgVecArgs va;
-    va.B = B; va.X = X; va.R = w.R; va.P = w.P; va.AP = w.AP;
+    va.B = B; va.X = w.Xd; va.R = w.R; va.P = w.P; va.AP = w.AP;
     va.n = a->m; va.k = k; va.part = w.part; va.ticket = a->ticket + 1;
 
-    rc = launch_vec(0, va, cg, max_iters);
+    rc = launch_vec(0, va, cg, max_iters, tol);
     if (rc) return rc;
 
     const bool use_graph = getenv("SMLE_NO_GRAPH") == nullptr;
-    if (use_graph && (!w.graph || w.graph_B != B || w.graph_X != X || w.graph_tol != tol ||
-                      w.graph_hist != want_hist)) {
-        if (w.graph) { cudaGraphExecDestroy(w.graph); w.graph = nullptr; }
+    if (use_graph && !w.graph) {
         // lazy setup (partition kernel, occupancy query) must happen outside the capture
         rc = launch_merge<double, true>(a, va.P, va.AP, k, cg, /*dry=*/true);
         if (rc) return rc;
@@ -420,7 +419,6 @@ int cg_solve_device(smle_csr_t a, const double *B, double *X, int k, int max_ite
         cudaGraphDestroy(graph);
         if (e != cudaSuccess) return fail(SMLE_ERR_CUDA, "graph instantiate failed: %s", cudaGetErrorString(e));
         w.graph_iters = kGraphIters;
-        w.graph_B = B; w.graph_X = X; w.graph_tol = tol; w.graph_hist = want_hist;
     }
 
     // Batches of iterations.  Batch j+1 is queued before the control words of batch j are
@@ -465,18 +463,21 @@ int cg_solve_device(smle_csr_t a, const double *B, double *X, int k, int max_ite
     cudaEventDestroy(ev[1]);
     if (rc) return rc;
 
-    // final state
-    double last_rel = 0.0;
+    // result + final state
+    const size_t xb = sizeof(double) * w.nk;
+    if (X_dev) CU(cudaMemcpyAsync(X_dev, w.Xd, xb, cudaMemcpyDeviceToDevice, g_stream));
+    if (X_host) CU(cudaMemcpyAsync(X_host, w.Xd, xb, cudaMemcpyDeviceToHost, g_stream));
     CU(cudaMemcpyAsync(w.ctrl_host, w.ctrl, sizeof(int) * CTRL_WORDS, cudaMemcpyDeviceToHost, g_stream));
-    CU(cudaMemcpyAsync(&last_rel, cg.last_rel, sizeof(double), cudaMemcpyDeviceToHost, g_stream));
+    CU(cudaMemcpyAsync(w.ctrl_host + CTRL_WORDS, cg.last_rel, sizeof(double), cudaMemcpyDeviceToHost, g_stream));
     CU(cudaStreamSynchronize(g_stream));
     int iters = w.ctrl_host[CTRL_ITER];
     if (iters_out) *iters_out = iters;
-    if (final_rel) *final_rel = last_rel;
+    if (final_rel) memcpy(final_rel, w.ctrl_host + CTRL_WORDS, sizeof(double));
     if (want_hist) {
         int nh = iters < w.hist_cap ? iters : w.hist_cap;
         if (nh > hist_capacity) nh = hist_capacity;
-        CU(cudaMemcpy(hist_out, w.hist, sizeof(double) * (size_t)nh, cudaMemcpyDeviceToHost));
+        CU(cudaMemcpyAsync(hist_out, w.hist, sizeof(double) * (size_t)nh, cudaMemcpyDeviceToHost, g_stream));
+        CU(cudaStreamSynchronize(g_stream));
         if (hist_len) *hist_len = nh;
     } else if (hist_len) {
         *hist_len = 0;
@@ -494,18 +495,13 @@ int cg_solve(smle_csr_t a, const double *B, double *X, int k, int max_iters, dou
     int rc = ensure_init();
     if (rc) return rc;
     if (is_device_ptr)
-        return cg_solve_device(a, B, X, k, max_iters, tol, iters_out, hist, hist_capacity, hist_len, final_rel);
+        return cg_solve_device(a, B, X, nullptr, k, max_iters, tol, iters_out, hist, hist_capacity, hist_len, final_rel);
     rc = ensure_workspace(a, k, 0);
     if (rc) return rc;
     CgWorkspace &w = a->ws;
-    size_t vb = sizeof(double) * (w.nk ? w.nk : 1);
-    if (!w.Bd) { CU(cudaMalloc(&w.Bd, vb)); CU(cudaMalloc(&w.Xd, vb)); }
+    if (!w.Bd) CU(cudaMalloc(&w.Bd, sizeof(double) * (w.nk ? w.nk : 1)));
     CU(cudaMemcpyAsync(w.Bd, B, sizeof(double) * w.nk, cudaMemcpyHostToDevice, g_stream));
-    rc = cg_solve_device(a, w.Bd, w.Xd, k, max_iters, tol, iters_out, hist, hist_capacity, hist_len, final_rel);
-    if (rc) return rc;
-    CU(cudaMemcpyAsync(X, w.Xd, sizeof(double) * w.nk, cudaMemcpyDeviceToHost, g_stream));
-    CU(cudaStreamSynchronize(g_stream));
-    return SMLE_OK;
+    return cg_solve_device(a, w.Bd, nullptr, X, k, max_iters, tol, iters_out, hist, hist_capacity, hist_len, final_rel);
 }
 
 } // namespace
@@ -674,6 +670,52 @@ int smle_cg_multi_f64(smle_csr_t a, const double *B, double *X, int k, int max_i
 int smle_cg_run_fixed_f64(smle_csr_t a, const double *B, double *X, int k, int iters)
 {
     return cg_solve(a, B, X, k, iters, -1.0, 1, nullptr, nullptr, 0, nullptr, nullptr);
+}
+
+int smle_cg_profile_f64(smle_csr_t a, const double *B, double *X, int k, int iters, float *ms_per_kernel)
+{
+    if (!a || !B || !X || k < 1 || iters < 1 || !ms_per_kernel) return fail(SMLE_ERR_ARG, "bad argument");
+    if (a->vbytes != 8 || a->m != a->n) return fail(SMLE_ERR_ARG, "CG needs a square fp64 handle");
+    int rc = ensure_init();
+    if (rc) return rc;
+    rc = ensure_workspace(a, k, 0);
+    if (!rc) rc = ensure_scratch(a, k);
+    if (rc) return rc;
+    CgWorkspace &w = a->ws;
+    CgScalars cg = make_scalars(w, k);
+    CgVecArgs va;
+    va.B = B; va.X = w.Xd; va.R = w.R; va.P = w.P; va.AP = w.AP;
+    va.n = a->m; va.k = k; va.part = w.part; va.ticket = a->ticket + 1;
+    (void)X;
+    rc = launch_merge<double, true>(a, va.P, va.AP, k, cg, /*dry=*/true);
+    if (!rc) rc = launch_vec(0, va, cg, iters + 2, -1.0);
+    if (rc) return rc;
+    std::vector<cudaEvent_t> ev((size_t)iters * 4);
+    for (auto &e : ev) CU(cudaEventCreate(&e));
+    rc = launch_iteration(a, va, cg);   // warm-up iteration, untimed
+    for (int i = 0; i < iters && !rc; ++i) {
+        CU(cudaEventRecord(ev[(size_t)i * 4 + 0], g_stream));
+        rc = launch_merge<double, true>(a, va.P, va.AP, k, cg);
+        CU(cudaEventRecord(ev[(size_t)i * 4 + 1], g_stream));
+        if (!rc) rc = launch_vec(1, va, cg);
+        CU(cudaEventRecord(ev[(size_t)i * 4 + 2], g_stream));
+        if (!rc) rc = launch_vec(2, va, cg);
+        CU(cudaEventRecord(ev[(size_t)i * 4 + 3], g_stream));
+    }
+    cudaError_t e = cudaStreamSynchronize(g_stream);
+    if (!rc && e != cudaSuccess) rc = fail(SMLE_ERR_CUDA, "sync failed: %s", cudaGetErrorString(e));
+    double acc[3] = {0, 0, 0};
+    if (!rc) {
+        for (int i = 0; i < iters; ++i)
+            for (int j = 0; j < 3; ++j) {
+                float ms = 0.f;
+                cudaEventElapsedTime(&ms, ev[(size_t)i * 4 + j], ev[(size_t)i * 4 + j + 1]);
+                acc[j] += ms;
+            }
+        for (int j = 0; j < 3; ++j) ms_per_kernel[j] = (float)(acc[j] / iters);
+    }
+    for (auto &ev1 : ev) cudaEventDestroy(ev1);
+    return rc;
 }
 
 } // extern "C"

@@ -66,7 +66,7 @@ __device__ __forceinline__ void publish_partials(double (&s)[VEC], int cb, int k
 // ---------------------------------------------------------------------------------------
 template <int G, int VEC>
 __global__ void __launch_bounds__(kThreads)
-cg_init_kernel(CgVecArgs a, CgScalars cg, int max_iters)
+cg_init_kernel(CgVecArgs a, CgScalars cg, int max_iters, double tol)
 {
     constexpr int W = kThreads / G, KB = G * VEC;
     __shared__ double s_w[kWarps][KB];
@@ -108,6 +108,7 @@ cg_init_kernel(CgVecArgs a, CgScalars cg, int max_iters)
         cg.ctrl[CTRL_MAX_ITERS] = max_iters;
         cg.ctrl[CTRL_NCONV] = 0;
         *cg.last_rel = 0.0;
+        *cg.tol = tol;
     }
 }
 
@@ -155,12 +156,13 @@ cg_update_r_kernel(CgVecArgs a, CgScalars cg)
 
     double worst = 0.0;
     int nconv = 0;
+    const double tol = *cg.tol;
     for (int c = tid; c < a.k; c += kThreads) {
         const double rn = cg.rs_new[c], ro = cg.rs_old[c];
         const double rel = sqrt(rn) / cg.bnorm[c];
         worst = fmax(worst, rel);
         int cv = cg.conv[c];
-        if (!cv && rel < cg.tol) { cv = 1; cg.conv[c] = 1; }
+        if (!cv && rel < tol) { cv = 1; cg.conv[c] = 1; }
         nconv += cv;
         cg.beta[c] = cv ? 0.0 : rn / ro;
         cg.rs_old[c] = rn;

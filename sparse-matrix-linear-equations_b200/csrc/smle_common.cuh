@@ -29,7 +29,7 @@ struct CgScalars {
     double *hist;      // max relative residual per iteration    (:150-155), nullable
     double *last_rel;  // max relative residual of the last iteration (1 double)
     int hist_cap;
-    double tol;
+    double *tol;       // relative tolerance, device resident so CUDA graphs stay valid across calls
 };
 
 // ---------------------------------------------------------------------------------------

@@ -246,6 +246,17 @@ class CsrMatrix:
         k = int(B.shape[1]) if B.dim() == 2 else 1
         _check(lib().smle_cg_run_fixed_f64(self._h, pB, pX, _I(k), _I(iters)))
 
+    def cg_profile(self, B, X, iters: int):
+        """mean ms of the three kernels of a CG iteration (CUDA events, no graph)."""
+        pB, dev, kB = _arg(B, np.float64)
+        pX, dev_x, kX = _arg(X, np.float64, writable=True)
+        if not (dev and dev_x):
+            raise SmleError("cg_profile needs device tensors")
+        k = int(B.shape[1]) if B.dim() == 2 else 1
+        out = (C.c_float * 3)()
+        _check(lib().smle_cg_profile_f64(self._h, pB, pX, _I(k), _I(iters), out))
+        return [float(v) for v in out]
+
 
 # ---------------------------------------------------------------------------------------------
 # generators (host side; CSR identical to reference generator + CsrMatrix::Init)

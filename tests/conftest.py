@@ -67,10 +67,26 @@ def named_matrix(gen, name):
     return table[name]()
 
 
-def rel_rownorm_err(Y, Y_ref):
-    """max over rows of |y - y_ref|_inf / |y_ref row|_2  (north_star: 'per row-norm')."""
-    Y = np.asarray(Y, dtype=np.float64).reshape(len(Y_ref), -1)
-    R = np.asarray(Y_ref, dtype=np.float64).reshape(len(Y_ref), -1)
+def rel_rownorm_err(Y, Y_ref, csr=None, X=None):
+    """north_star's "relative per row-norm" error:  max_i |y_i - yref_i| / scale_i.
+
+    With csr=(row_offsets, column_indices, values) and X given, scale = (|A| |X|)_i -- the
+    magnitude the row's dot product is built from (the standard componentwise bound for a
+    rounding-order difference); otherwise scale_i = ||yref row i||_2 (only meaningful when no
+    cancellation occurs, e.g. the golden vectors)."""
+    R = np.asarray(Y_ref, dtype=np.float64)
+    R = R.reshape(len(R), -1)
+    Y = np.asarray(Y, dtype=np.float64).reshape(R.shape)
+    if not len(R):
+        return 0.0
+    if csr is not None:
+        import scipy.sparse as sp
+        ro, ci, va = csr
+        Xa = np.abs(np.asarray(X, dtype=np.float64)).reshape(-1, R.shape[1])
+        A = sp.csr_matrix((np.abs(va.astype(np.float64)), ci, ro), shape=(len(ro) - 1, Xa.shape[0]))
+        scale = A @ Xa
+        scale[scale == 0] = 1.0
+        return float((np.abs(Y - R) / scale).max())
     norm = np.linalg.norm(R, axis=1)
     norm[norm == 0] = 1.0
-    return float((np.abs(Y - R).max(axis=1) / norm).max()) if len(R) else 0.0
+    return float((np.abs(Y - R).max(axis=1) / norm).max())

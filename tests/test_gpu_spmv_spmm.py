@@ -34,8 +34,8 @@ def test_golden_spmv(gpu, golden):
         ncols = len(x)
         a = gpu.CsrMatrix(ro, ci, va, ncols)
         y = a.spmv(x)
-        assert rel_rownorm_err(y, np.array(rec["y"])) <= 1e-12, rec["matrix"]
-        assert rel_rownorm_err(y, np.array(rec["y_gold"])) <= 1e-12, rec["matrix"]
+        assert rel_rownorm_err(y, np.array(rec["y"]), (ro, ci, va), x) <= 1e-12, rec["matrix"]
+        assert rel_rownorm_err(y, np.array(rec["y_gold"]), (ro, ci, va), x) <= 1e-12, rec["matrix"]
         a.close()
 
 
@@ -45,7 +45,7 @@ def test_golden_spmm(gpu, golden):
         X = np.array(rec["X"]).reshape(-1, rec["k"])
         a = gpu.CsrMatrix(ro, ci, va, X.shape[0])
         Y = a.spmm(X)
-        assert rel_rownorm_err(Y, np.array(rec["Y"]).reshape(-1, rec["k"])) <= 1e-12, (rec["matrix"], rec["k"])
+        assert rel_rownorm_err(Y, np.array(rec["Y"]).reshape(-1, rec["k"]), (ro, ci, va), X) <= 1e-12, (rec["matrix"], rec["k"])
         a.close()
 
 
@@ -57,8 +57,8 @@ def test_spmv_against_oracle(gpu, orc, dtype):
         x = rng.random(max(m, n)).astype(dtype)
         a = gpu.CsrMatrix(ro, ci, va, len(x))
         y = a.spmv(x)
-        assert rel_rownorm_err(y, orc.spmv_gold(ro, ci, va, x)) <= TOL[dtype], name
-        assert rel_rownorm_err(y, orc.merge_csrmv(8, ro, ci, va, x)) <= TOL[dtype], name
+        assert rel_rownorm_err(y, orc.spmv_gold(ro, ci, va, x), (ro, ci, va), x) <= TOL[dtype], name
+        assert rel_rownorm_err(y, orc.merge_csrmv(8, ro, ci, va, x), (ro, ci, va), x) <= TOL[dtype], name
         a.close()
 
 
@@ -73,7 +73,7 @@ def test_spmm_against_oracle(gpu, orc, dtype, k):
         X = (rng.random((max(m, n), k)) - 0.5).astype(dtype)
         a = gpu.CsrMatrix(ro, ci, va, X.shape[0])
         Y = a.spmm(X)
-        assert rel_rownorm_err(Y, orc.merge_csrmm(8, ro, ci, va, X, k)) <= TOL[dtype], (name, k)
+        assert rel_rownorm_err(Y, orc.merge_csrmm(8, ro, ci, va, X, k), (ro, ci, va), X) <= TOL[dtype], (name, k)
         a.close()
 
 
@@ -83,9 +83,9 @@ def test_empty_rows_long_row_and_rectangular(gpu, orc, dtype):
     ro, ci, va = _with_empty_rows(rng, 3000, 777, dtype)
     a = gpu.CsrMatrix(ro, ci, va, 777)
     x = rng.random(777).astype(dtype)
-    assert rel_rownorm_err(a.spmv(x), orc.spmv_gold(ro, ci, va, x, n=777)) <= TOL[dtype]
+    assert rel_rownorm_err(a.spmv(x), orc.spmv_gold(ro, ci, va, x, n=777), (ro, ci, va), x) <= TOL[dtype]
     X = rng.random((777, 6)).astype(dtype)
-    assert rel_rownorm_err(a.spmm(X), orc.merge_csrmm(4, ro, ci, va, X, 6, n=777)) <= TOL[dtype]
+    assert rel_rownorm_err(a.spmm(X), orc.merge_csrmm(4, ro, ci, va, X, 6, n=777), (ro, ci, va), X) <= TOL[dtype]
     a.close()
 
 
@@ -112,7 +112,7 @@ def test_device_pointers_and_determinism(gpu, orc):
     Y2 = a.spmm(X)
     gpu.sync()
     assert torch.equal(Y1, Y2), "SpMM must be deterministic run to run"
-    assert rel_rownorm_err(Y1.cpu().numpy(), orc.merge_csrmm(8, ro, ci, va, X.cpu().numpy(), 8)) <= 1e-12
+    assert rel_rownorm_err(Y1.cpu().numpy(), orc.merge_csrmm(8, ro, ci, va, X.cpu().numpy(), 8), (ro, ci, va), X.cpu().numpy()) <= 1e-12
     a.close()
 
 
