@@ -18,6 +18,7 @@
 
 #include "smle_cg.cuh"
 #include "smle_merge.cuh"
+#include "smle_spmv.cuh"
 
 using namespace smle;
 
@@ -222,9 +223,51 @@ int launch_merge_t(smle_csr_t a, const V *X, V *Y, int k, const CgScalars &cg, b
     return check_launch("merge_kernel");
 }
 
+// k == 1: the TMA-staged single-vector kernel (smle_spmv.cuh)
+constexpr int kSpmvIPT = 12;      // merge items per thread per tile
+constexpr int kSpmvStages = 2;    // tiles in flight per CTA
+
+template <typename V, bool DOT>
+int launch_spmv(smle_csr_t a, const V *x, V *y, const CgScalars &cg, bool dry)
+{
+    using SM = SpmvSmem<V, kSpmvIPT>;
+    constexpr size_t smem = SM::STAGE_BYTES * kSpmvStages;
+    auto kern = spmv_kernel<V, kSpmvIPT, kSpmvStages, DOT>;
+    Partition *p;
+    int rc = get_partition(a, SM::TILE, &p);
+    if (rc) return rc;
+    rc = ensure_scratch(a, 1);
+    if (rc) return rc;
+    static int occ = 0;   // per instantiation
+    if (!occ) {
+        CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kThreads, smem));
+        if (occ < 1) return fail(SMLE_ERR_CUDA, "spmv_kernel does not fit on an SM (%zu B smem)", smem);
+        if (occ > 8) occ = 8;
+    }
+    if (dry) return SMLE_OK;
+    int max_ctas = g_sms * occ;
+    if (max_ctas > a->max_ctas) max_ctas = a->max_ctas;
+    int grid = p->num_tiles < max_ctas ? p->num_tiles : max_ctas;
+    int tiles_per_cta = (p->num_tiles + grid - 1) / grid;
+    grid = (p->num_tiles + tiles_per_cta - 1) / tiles_per_cta;
+    SpmvArgs<V> args;
+    args.ro = a->ro; args.ci = a->ci; args.va = (const V *)a->va;
+    args.x = x; args.y = y; args.tile_xy = p->xy;
+    args.m = a->m; args.nnz = a->nnz;
+    args.num_tiles = p->num_tiles; args.tiles_per_cta = tiles_per_cta;
+    args.carry_row = a->carry_row; args.carry_val = (V *)a->carry_val;
+    args.dot_part = (V *)a->dot_part; args.fix_part = (V *)a->fix_part;
+    args.ticket = a->ticket;
+    kern<<<grid, kThreads, smem, g_stream>>>(args, cg);
+    ++g_launches;
+    return check_launch("spmv_kernel");
+}
+
 template <typename V, bool DOT>
 int launch_merge(smle_csr_t a, const V *X, V *Y, int k, const CgScalars &cg, bool dry = false)
 {
+    if (k == 1 && getenv("SMLE_SPMV_V1") == nullptr) return launch_spmv<V, DOT>(a, X, Y, cg, dry);
     int G, VEC;
     pick_shape<V>(k, &G, &VEC);
 #define SMLE_CASE(g, v) \
@@ -636,7 +679,7 @@ int smle_csr_tile_coords(smle_csr_t a, int k, int *num_tiles, int *items_per_til
     int rc = ensure_init();
     if (rc) return rc;
     Partition *p;
-    rc = get_partition(a, kTileItems, &p);
+    rc = get_partition(a, k == 1 ? kThreads * kSpmvIPT : kTileItems, &p);
     if (rc) return rc;
     if (num_tiles) *num_tiles = p->num_tiles;
     if (items_per_tile) *items_per_tile = p->items_per_tile;

@@ -1,0 +1,382 @@
+// smle_spmv.cuh -- single-vector merge-path SpMV for sm_100a (k = 1 fast path).
+//
+// Replaces OmpMergeCsrmv (reference cpu_spmv.cpp:360-421) and the SpMV inside CGSolveSingle
+// (work_2025/main/single_strategy.hpp:137).  Same merge-path decomposition as smle_merge.cuh,
+// but laid out for one right-hand side, where the kernel is a pure HBM stream of the CSR arrays
+// (12 B per nonzero in fp64) plus an L1/L2-resident gather of x:
+//
+//   * persistent CTAs, each owning a contiguous run of tiles of TILE = 256*IPT merge items;
+//   * the tile's column indices, values and row offsets are brought into shared memory by the
+//     TMA engine (cp.async.bulk, 1-D, completion on an mbarrier) STAGES tiles ahead of the
+//     compute, with an L2 evict-first policy -- the matrix is streamed once per SpMV and must
+//     not push the CG vectors out of the 126 MB L2;
+//   * phase A (coalesced, branch-free): every staged nonzero becomes value * x[column], written
+//     back in place; 128-bit shared-memory accesses, all gathers of a thread issued back to back;
+//   * phase B: each thread finds its diagonal with the reference's binary search (in shared
+//     memory) and reduces exactly IPT merge items; completed rows go to a shared row buffer,
+//     the first row of every thread waits for its carry-in;
+//   * carries: warp-shuffle segmented scan keyed by row -> per-tile -> per-CTA -> the last CTA
+//     to finish applies the per-CTA carries in CTA order (merge_based.hpp:137-149 semantics);
+//   * phase C: the tile's rows are written to y with coalesced stores; with DOT the products
+//     y[r]*x[r] (the p.Ap of CG) are accumulated from the same registers.
+#pragma once
+#include "smle_common.cuh"
+#include "smle_merge.cuh"
+
+namespace smle {
+
+// ---- PTX wrappers: mbarrier + 1-D bulk async copy (TMA) ---------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p)
+{
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+
+__device__ __forceinline__ uint64_t l2_policy_evict_first()
+{
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+
+__device__ __forceinline__ uint64_t l2_policy_evict_last()
+{
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+
+// global -> shared bulk copy; src and dst 16-byte aligned, bytes a multiple of 16
+__device__ __forceinline__ void tma_load_1d(void *dst, const void *src, uint32_t bytes, uint64_t *bar,
+                                            uint64_t policy)
+{
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+            smem_u32(dst)),
+        "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+        : "memory");
+}
+
+__device__ __forceinline__ void fence_proxy_async()
+{
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
+template <typename V>
+struct SpmvArgs {
+    const int *__restrict__ ro;        // row offsets (m + 1 entries, 16 B of slack behind)
+    const int *__restrict__ ci;
+    const V *__restrict__ va;
+    const V *__restrict__ x;
+    V *__restrict__ y;
+    const int2 *__restrict__ tile_xy;  // num_tiles + 1 merge-path coordinates
+    int m, nnz;
+    int num_tiles, tiles_per_cta;
+    int *carry_row;                    // [gridDim.x]
+    V *carry_val;                      // [gridDim.x]
+    V *dot_part;                       // [gridDim.x]  (DOT)
+    V *fix_part;                       // [gridDim.x]  (DOT)
+    unsigned int *ticket;
+};
+
+template <typename V, int IPT>
+struct SpmvSmem {
+    static constexpr int TILE = kThreads * IPT;
+    static constexpr int EPV = 16 / (int)sizeof(V);                  // values per 16 bytes
+    static constexpr int COL_WORDS = TILE + 8;                       // staged column indices
+    static constexpr int VAL_ELEMS = TILE + 2 * EPV;                 // staged values
+    static constexpr int RO_WORDS = TILE + 8;                        // staged row offsets
+    static constexpr size_t STAGE_BYTES =
+        ((size_t)COL_WORDS * 4 + (size_t)VAL_ELEMS * sizeof(V) + (size_t)RO_WORDS * 4 + 15) / 16 * 16;
+    // the row buffer of phase B/C aliases the column-index region (free after phase A)
+    static constexpr int YBUF_ROWS = (COL_WORDS * 4) / (int)sizeof(V);
+};
+
+template <typename V, int IPT, int STAGES, bool DOT>
+__global__ void __launch_bounds__(kThreads)
+spmv_kernel(SpmvArgs<V> a, CgScalars cg)
+{
+    using SM = SpmvSmem<V, IPT>;
+    constexpr int TILE = SM::TILE;
+    constexpr int EPV = SM::EPV;
+
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ uint64_t s_full[STAGES];
+    __shared__ int s_wkey_first[kWarps], s_wkey_last[kWarps];
+    __shared__ V s_wsum[kWarps], s_wfull[kWarps];
+    __shared__ V s_carry;
+    __shared__ V s_red[kThreads];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    if constexpr (DOT) {
+        if (cg.ctrl[CTRL_STOP]) {
+            if (blockIdx.x == 0 && tid == 0) cg.ctrl[CTRL_HALT] = 1;
+            return;
+        }
+    }
+
+    const int t0 = blockIdx.x * a.tiles_per_cta;
+    const int t1 = min(t0 + a.tiles_per_cta, a.num_tiles);
+
+    auto stage_col = [&](int s) { return reinterpret_cast<int *>(smem_raw + (size_t)s * SM::STAGE_BYTES); };
+    auto stage_val = [&](int s) {
+        return reinterpret_cast<V *>(smem_raw + (size_t)s * SM::STAGE_BYTES + (size_t)SM::COL_WORDS * 4);
+    };
+    auto stage_ro = [&](int s) {
+        return reinterpret_cast<int *>(smem_raw + (size_t)s * SM::STAGE_BYTES + (size_t)SM::COL_WORDS * 4 +
+                                       (size_t)SM::VAL_ELEMS * sizeof(V));
+    };
+
+    // producer: one thread arms the stage's mbarrier and issues the three bulk copies of a tile
+    const uint64_t pol_stream = l2_policy_evict_first();
+    auto issue = [&](int t, int s) {
+        const int2 lo = a.tile_xy[t], hi = a.tile_xy[t + 1];
+        const int yc = lo.y & ~3;                                   // 16 B aligned column start
+        const int yv = lo.y & ~(EPV - 1);                           // 16 B aligned value start
+        const int rb = (lo.x + 1) & ~3;                             // 16 B aligned row-offset start
+        const uint32_t nb_col = (uint32_t)((hi.y - yc + 3) & ~3) * 4u;
+        const uint32_t nb_val = (uint32_t)((hi.y - yv + EPV - 1) & ~(EPV - 1)) * (uint32_t)sizeof(V);
+        const uint32_t nb_ro = (uint32_t)((hi.x + 2 - rb + 3) & ~3) * 4u;
+        const uint32_t total = nb_col + nb_val + nb_ro;             // nb_ro > 0 always
+        mbar_expect_tx(&s_full[s], total);
+        if (nb_col) tma_load_1d(stage_col(s), a.ci + yc, nb_col, &s_full[s], pol_stream);
+        if (nb_val) tma_load_1d(stage_val(s), a.va + yv, nb_val, &s_full[s], pol_stream);
+        tma_load_1d(stage_ro(s), a.ro + rb, nb_ro, &s_full[s], pol_stream);
+    };
+
+    if (tid == 0) {
+        for (int s = 0; s < STAGES; ++s) mbar_init(&s_full[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        s_carry = 0;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        for (int s = 0; s < STAGES && t0 + s < t1; ++s) issue(t0 + s, s);
+    }
+
+    V dot = 0;
+    V carry_out = 0;
+    int last_key = a.m;
+
+    for (int t = t0; t < t1; ++t) {
+        const int it = t - t0, s = it % STAGES;
+        const uint32_t parity = (uint32_t)(it / STAGES) & 1u;
+        const int2 lo = a.tile_xy[t], hi = a.tile_xy[t + 1];
+        const int x0 = lo.x, y0 = lo.y;
+        const int rows = hi.x - x0, nz = hi.y - y0, items = rows + nz;
+        const int yc = y0 & ~3, yv = y0 & ~(EPV - 1), rb = (x0 + 1) & ~3;
+        int *s_col = stage_col(s);
+        V *s_val = stage_val(s);
+        const int *s_ro = stage_ro(s);
+        V *s_y = reinterpret_cast<V *>(s_col);        // row buffer, valid after phase A
+        const bool y_in_smem = rows <= SM::YBUF_ROWS;
+
+        mbar_wait(&s_full[s], parity);
+
+        // ---- phase A: products in place ------------------------------------------------------
+        // all shared loads and all gathers of a thread are issued before the first product is
+        // written back, so MAXIT*EPV independent global loads are in flight per thread
+        {
+            const int nvec = (hi.y - yv + EPV - 1) / EPV;   // 16-byte groups staged
+            constexpr int MAXIT = (SM::VAL_ELEMS / EPV + kThreads - 1) / kThreads;
+            V v[MAXIT][EPV];
+            V xv[MAXIT][EPV];
+#pragma unroll
+            for (int q = 0; q < MAXIT; ++q) {
+                const int g = tid + q * kThreads;           // group index
+                if (g < nvec) {
+                    int c[EPV];
+                    ld_vec<V, EPV>(v[q], s_val + g * EPV);
+                    const int cbase = yv + g * EPV - yc;    // index into s_col (multiple of EPV)
+                    if constexpr (EPV == 2) {
+                        int2 cc = *reinterpret_cast<const int2 *>(s_col + cbase);
+                        c[0] = cc.x; c[1] = cc.y;
+                    } else {
+                        int4 cc = *reinterpret_cast<const int4 *>(s_col + cbase);
+                        c[0] = cc.x; c[1] = cc.y; c[2] = cc.z; c[3] = cc.w;
+                    }
+#pragma unroll
+                    for (int e = 0; e < EPV; ++e) {
+                        const int gi = yv + g * EPV + e;    // global nonzero index
+                        xv[q][e] = (gi >= y0 && gi < hi.y) ? __ldg(a.x + c[e]) : V(0);
+                    }
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < MAXIT; ++q) {
+                const int g = tid + q * kThreads;
+                if (g < nvec) {
+#pragma unroll
+                    for (int e = 0; e < EPV; ++e) v[q][e] *= xv[q][e];
+                    st_vec<V, EPV>(s_val + g * EPV, v[q]);
+                }
+            }
+        }
+        __syncthreads();
+
+        // ---- phase B: per-thread merge walk over IPT items -------------------------------------
+        const int d0 = min(tid * IPT, items);
+        int r;
+        {
+            int l = max(d0 - nz, 0), h = min(d0, rows);
+            while (l < h) {
+                int mid = (l + h) >> 1;
+                if (s_ro[x0 + mid + 1 - rb] - y0 <= d0 - mid - 1) l = mid + 1; else h = mid;
+            }
+            r = l;
+        }
+        int z = d0 - r;
+        const int voff = y0 - yv;
+        V acc = (tid == 0) ? s_carry : V(0);
+        V first_acc = 0;
+        int first_row = -1;
+        int cur_end = s_ro[x0 + r + 1 - rb] - y0;
+        const int n_items = min(IPT, items - d0);
+#pragma unroll
+        for (int i = 0; i < IPT; ++i) {
+            if (i < n_items) {
+                if (z < cur_end) {
+                    acc += s_val[voff + z];
+                    ++z;
+                } else {
+                    if (first_row < 0) { first_row = r; first_acc = acc; }
+                    else if (y_in_smem) s_y[r] = acc;
+                    else a.y[x0 + r] = acc;
+                    acc = 0;
+                    ++r;
+                    cur_end = s_ro[x0 + r + 1 - rb] - y0;
+                }
+            }
+        }
+
+        // ---- carries: inclusive segmented scan keyed by the row in progress ----------------------
+        const int key = x0 + r;
+        V sc = acc;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int okey = __shfl_up_sync(0xffffffffu, key, d);
+            const V o = __shfl_up_sync(0xffffffffu, sc, d);
+            if (lane >= d && okey == key) sc += o;
+        }
+        if (lane == 31) { s_wkey_last[warp] = key; s_wsum[warp] = sc; }
+        if (lane == 0) s_wkey_first[warp] = key;
+        __syncthreads();
+        if (tid == 0) {
+            // full inclusive value of each warp's last thread (chains across warps of one row)
+            V f = 0;
+            for (int wi = 0; wi < kWarps; ++wi) {
+                const bool chain = wi > 0 && s_wkey_first[wi] == s_wkey_last[wi] &&
+                                   s_wkey_last[wi - 1] == s_wkey_last[wi];
+                f = s_wsum[wi] + (chain ? f : V(0));
+                s_wfull[wi] = f;
+            }
+        }
+        __syncthreads();
+        const V wprev = warp > 0 ? s_wfull[warp - 1] : V(0);
+        const int wprev_key = warp > 0 ? s_wkey_last[warp - 1] : -1;
+        const int wfirst_key = s_wkey_first[warp];
+        // my full inclusive value: add the previous warps' chain when it reaches me
+        V sfull = sc + ((wfirst_key == key && wprev_key == key) ? wprev : V(0));
+        V carry_in = __shfl_up_sync(0xffffffffu, sfull, 1);
+        if (lane == 0) carry_in = wprev;
+        if (tid == 0) carry_in = 0;   // the CTA carry already seeded thread 0's accumulator
+        if (first_row >= 0) {
+            const V vfirst = first_acc + carry_in;
+            if (y_in_smem) s_y[first_row] = vfirst;
+            else a.y[x0 + first_row] = vfirst;
+        }
+        if (tid == kThreads - 1) {
+            s_carry = sfull;          // tile carry-out (row hi.x)
+            carry_out = sfull;
+            last_key = key;
+        }
+        __syncthreads();
+
+        // ---- phase C: coalesced row output (+ dot) -----------------------------------------------
+        if (y_in_smem) {
+            for (int i = tid; i < rows; i += kThreads) {
+                const V v = s_y[i];
+                a.y[x0 + i] = v;
+                if constexpr (DOT) dot += v * __ldg(a.x + x0 + i);
+            }
+        } else if constexpr (DOT) {
+            __threadfence_block();
+            for (int i = tid; i < rows; i += kThreads) dot += a.y[x0 + i] * __ldg(a.x + x0 + i);
+        }
+        __syncthreads();   // stage s fully consumed
+
+        if (tid == 0 && t + STAGES < t1) {
+            fence_proxy_async();
+            issue(t + STAGES, s);
+        }
+    }
+
+    // ---- CTA carry-out ---------------------------------------------------------------------------
+    if (tid == kThreads - 1) {
+        a.carry_row[blockIdx.x] = (t1 > t0) ? last_key : a.m;
+        a.carry_val[blockIdx.x] = (t1 > t0) ? carry_out : V(0);
+    }
+
+    if constexpr (DOT) {
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, d);
+        if (lane == 0) s_wsum[warp] = dot;
+        __syncthreads();
+        if (tid == 0) {
+            V sdot = 0;
+            for (int wi = 0; wi < kWarps; ++wi) sdot += s_wsum[wi];
+            a.dot_part[blockIdx.x] = sdot;
+        }
+    }
+
+    // ---- last CTA done: serial-order carry fix-up (merge_based.hpp:137-149) ----------------------
+    if (!last_cta_election(a.ticket, gridDim.x)) return;
+
+    const int entries = gridDim.x;
+    for (int e = tid; e < entries; e += kThreads) {
+        const int row = __ldcg(a.carry_row + e);
+        V fixdot = 0;
+        if (row < a.m && (e == 0 || __ldcg(a.carry_row + e - 1) != row)) {
+            V sum = 0;
+            for (int e2 = e; e2 < entries && __ldcg(a.carry_row + e2) == row; ++e2)
+                sum += __ldcg(a.carry_val + e2);
+            a.y[row] = __ldcg(a.y + row) + sum;
+            if constexpr (DOT) fixdot = sum * __ldg(a.x + row);
+        }
+        if constexpr (DOT) a.fix_part[e] = fixdot;
+    }
+    if constexpr (DOT) {
+        __syncthreads();
+        cta_reduce_columns<V>(a.dot_part, a.fix_part, entries, 1, (V *)cg.pAp, s_red);
+        if (tid == 0) cg.alpha[0] = cg.conv[0] ? 0.0 : cg.rs_old[0] / cg.pAp[0];
+    }
+}
+
+} // namespace smle

@@ -59,6 +59,15 @@ def _check(rc: int):
         raise SmleError(f"smle status {rc}: {lib().smle_last_error().decode()}")
 
 
+def _publish(dev: int) -> None:
+    """Device outputs were written on the library's stream: unless the caller shares that stream
+    (set_stream), wait for them so that torch ops on other streams see finished data."""
+    if dev:
+        import torch
+        if torch.cuda.current_stream().cuda_stream != get_stream():
+            sync()
+
+
 def device_count() -> int:
     return int(lib().smle_device_count())
 
@@ -103,6 +112,12 @@ def _arg(x, dtype, writable=False):
                 np.dtype(np.int32): torch.int32}[np.dtype(dtype)]
         if x.dtype != want or not x.is_contiguous():
             raise SmleError(f"tensor must be contiguous {want}")
+        if x.is_cuda and not writable:
+            # inputs produced on torch's current stream must be complete before the library's
+            # stream reads them (no-op when the caller shares its stream through set_stream)
+            cur = torch.cuda.current_stream(x.device)
+            if cur.cuda_stream != get_stream():
+                cur.synchronize()
         return _P(x.data_ptr()), (1 if x.is_cuda else 0), x
     a = np.ascontiguousarray(x, dtype=dtype)
     if writable and a is not x:
@@ -192,6 +207,7 @@ class CsrMatrix:
         if dev != dev_y:
             raise SmleError("x and y must both be host or both be device memory")
         _check(getattr(lib(), f"smle_spmv_{self._s}")(self._h, px, py, _I(dev)))
+        _publish(dev)
         return y
 
     def spmm(self, X, out=None):
@@ -203,6 +219,7 @@ class CsrMatrix:
         if dev != dev_y:
             raise SmleError("X and Y must both be host or both be device memory")
         _check(getattr(lib(), f"smle_spmm_{self._s}")(self._h, pX, pY, _I(k), _I(dev)))
+        _publish(dev)
         return Y
 
     # -- CG -------------------------------------------------------------------------------------
