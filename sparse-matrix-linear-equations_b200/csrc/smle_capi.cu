@@ -305,6 +305,9 @@ int csr_create(smle_csr_t *out, int m, int n, int nnz, const int *ro, const int 
         smle_csr_destroy(a);
         return fail(SMLE_ERR_ALLOC, "device allocation failed: %s", cudaGetErrorString(e));
     }
+    cudaMemsetAsync((char *)a->ro + sizeof(int) * ((size_t)m + 1), 0, 16, g_stream);
+    cudaMemsetAsync((char *)a->ci + sizeof(int) * (size_t)nnz, 0, 16, g_stream);
+    cudaMemsetAsync((char *)a->va + sizeof(V) * (size_t)nnz, 0, 16, g_stream);
     if ((e = cudaMemcpyAsync(a->ro, ro, sizeof(int) * ((size_t)m + 1), cudaMemcpyHostToDevice, g_stream)) != cudaSuccess ||
         (e = cudaMemcpyAsync(a->ci, ci, sizeof(int) * (size_t)nnz, cudaMemcpyHostToDevice, g_stream)) != cudaSuccess ||
         (e = cudaMemcpyAsync(a->va, va, sizeof(V) * (size_t)nnz, cudaMemcpyHostToDevice, g_stream)) != cudaSuccess ||

@@ -129,9 +129,10 @@ spmv_kernel(SpmvArgs<V> a, CgScalars cg)
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ uint64_t s_full[STAGES];
     __shared__ int s_wkey_first[kWarps], s_wkey_last[kWarps];
-    __shared__ V s_wsum[kWarps], s_wfull[kWarps];
+    __shared__ V s_wsum[kWarps];
     __shared__ V s_carry;
     __shared__ V s_red[kThreads];
+    __shared__ int s_rstart[kThreads + 1];   // rows consumed before each thread's diagonal
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
@@ -202,32 +203,43 @@ spmv_kernel(SpmvArgs<V> a, CgScalars cg)
 
         // ---- phase A: products in place ------------------------------------------------------
         // all shared loads and all gathers of a thread are issued before the first product is
-        // written back, so MAXIT*EPV independent global loads are in flight per thread
+        // written back, so MAXIT*EPV independent global loads are in flight per thread.  The
+        // 16-byte groups at the edges may include nonzeros of the neighbouring tiles: their
+        // products are computed (the column is valid; the slack behind ci is zero-filled) and
+        // never read.
         {
             const int nvec = (hi.y - yv + EPV - 1) / EPV;   // 16-byte groups staged
             constexpr int MAXIT = (SM::VAL_ELEMS / EPV + kThreads - 1) / kThreads;
             V v[MAXIT][EPV];
             V xv[MAXIT][EPV];
+            const int cshift = yv - yc;                     // s_col index of value group 0
 #pragma unroll
             for (int q = 0; q < MAXIT; ++q) {
                 const int g = tid + q * kThreads;           // group index
                 if (g < nvec) {
                     int c[EPV];
                     ld_vec<V, EPV>(v[q], s_val + g * EPV);
-                    const int cbase = yv + g * EPV - yc;    // index into s_col (multiple of EPV)
                     if constexpr (EPV == 2) {
-                        int2 cc = *reinterpret_cast<const int2 *>(s_col + cbase);
+                        int2 cc = *reinterpret_cast<const int2 *>(s_col + cshift + g * EPV);
                         c[0] = cc.x; c[1] = cc.y;
                     } else {
-                        int4 cc = *reinterpret_cast<const int4 *>(s_col + cbase);
+                        int4 cc = *reinterpret_cast<const int4 *>(s_col + cshift + g * EPV);
                         c[0] = cc.x; c[1] = cc.y; c[2] = cc.z; c[3] = cc.w;
                     }
 #pragma unroll
-                    for (int e = 0; e < EPV; ++e) {
-                        const int gi = yv + g * EPV + e;    // global nonzero index
-                        xv[q][e] = (gi >= y0 && gi < hi.y) ? __ldg(a.x + c[e]) : V(0);
-                    }
+                    for (int e = 0; e < EPV; ++e) xv[q][e] = __ldg(a.x + c[e]);
                 }
+            }
+            // while the gathers fly: scatter the row-end markers to the threads that start
+            // behind them.  Marker of local row i sits at merge position pos_i = nnz_before + i;
+            // thread t (diagonal t*IPT) has consumed r_t = #{i : pos_i < t*IPT} rows.  This
+            // equals MergePathSearch(t*IPT) of the reference without a per-thread bisection.
+            for (int i = tid; i <= rows; i += kThreads) {
+                const int prev = (i == 0) ? -1 : (s_ro[x0 + i - rb] - y0) + (i - 1);
+                const int pos = (i == rows) ? (kThreads * IPT + IPT) : (s_ro[x0 + i + 1 - rb] - y0) + i;
+                int tlo = (prev + IPT) / IPT;
+                int thi = min(pos / IPT, kThreads);
+                for (int tt = tlo; tt <= thi; ++tt) s_rstart[tt] = i;
             }
 #pragma unroll
             for (int q = 0; q < MAXIT; ++q) {
@@ -241,76 +253,64 @@ spmv_kernel(SpmvArgs<V> a, CgScalars cg)
         }
         __syncthreads();
 
-        // ---- phase B: per-thread merge walk over IPT items -------------------------------------
+        // ---- phase B: per-thread merge walk over IPT items (predicated, no divergence) ----------
         const int d0 = min(tid * IPT, items);
-        int r;
-        {
-            int l = max(d0 - nz, 0), h = min(d0, rows);
-            while (l < h) {
-                int mid = (l + h) >> 1;
-                if (s_ro[x0 + mid + 1 - rb] - y0 <= d0 - mid - 1) l = mid + 1; else h = mid;
-            }
-            r = l;
-        }
+        const int r_start = min(s_rstart[tid], rows);
+        int r = r_start;
         int z = d0 - r;
         const int voff = y0 - yv;
         V acc = (tid == 0) ? s_carry : V(0);
-        V first_acc = 0;
-        int first_row = -1;
         int cur_end = s_ro[x0 + r + 1 - rb] - y0;
         const int n_items = min(IPT, items - d0);
 #pragma unroll
         for (int i = 0; i < IPT; ++i) {
-            if (i < n_items) {
-                if (z < cur_end) {
-                    acc += s_val[voff + z];
-                    ++z;
-                } else {
-                    if (first_row < 0) { first_row = r; first_acc = acc; }
-                    else if (y_in_smem) s_y[r] = acc;
-                    else a.y[x0 + r] = acc;
-                    acc = 0;
-                    ++r;
-                    cur_end = s_ro[x0 + r + 1 - rb] - y0;
-                }
+            const bool live = i < n_items;
+            const bool is_nz = live && (z < cur_end);
+            const V pv = s_val[voff + z];             // always in bounds of the stage buffer
+            if (is_nz) { acc += pv; ++z; }
+            if (live && !is_nz) {
+                if (y_in_smem) s_y[r] = acc; else a.y[x0 + r] = acc;
+                acc = 0;
+                ++r;
+                cur_end = s_ro[x0 + r + 1 - rb] - y0;
             }
         }
 
         // ---- carries: inclusive segmented scan keyed by the row in progress ----------------------
         const int key = x0 + r;
         V sc = acc;
+        {
+            const int pkey = __shfl_up_sync(0xffffffffu, key, 1);
+            const bool same = lane > 0 && pkey == key;
+            if (__any_sync(0xffffffffu, same)) {   // some row spans several threads of this warp
 #pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const int okey = __shfl_up_sync(0xffffffffu, key, d);
-            const V o = __shfl_up_sync(0xffffffffu, sc, d);
-            if (lane >= d && okey == key) sc += o;
+                for (int d = 1; d < 32; d <<= 1) {
+                    const int okey = __shfl_up_sync(0xffffffffu, key, d);
+                    const V o = __shfl_up_sync(0xffffffffu, sc, d);
+                    if (lane >= d && okey == key) sc += o;
+                }
+            }
         }
         if (lane == 31) { s_wkey_last[warp] = key; s_wsum[warp] = sc; }
         if (lane == 0) s_wkey_first[warp] = key;
         __syncthreads();
-        if (tid == 0) {
-            // full inclusive value of each warp's last thread (chains across warps of one row)
-            V f = 0;
-            for (int wi = 0; wi < kWarps; ++wi) {
-                const bool chain = wi > 0 && s_wkey_first[wi] == s_wkey_last[wi] &&
-                                   s_wkey_last[wi - 1] == s_wkey_last[wi];
-                f = s_wsum[wi] + (chain ? f : V(0));
-                s_wfull[wi] = f;
-            }
+        // full inclusive value of the previous warps' last threads (a row may chain across warps)
+        V wprev = 0;
+        for (int wi = 0; wi < warp; ++wi) {
+            const bool chain = wi > 0 && s_wkey_first[wi] == s_wkey_last[wi] &&
+                               s_wkey_last[wi - 1] == s_wkey_last[wi];
+            wprev = s_wsum[wi] + (chain ? wprev : V(0));
         }
-        __syncthreads();
-        const V wprev = warp > 0 ? s_wfull[warp - 1] : V(0);
         const int wprev_key = warp > 0 ? s_wkey_last[warp - 1] : -1;
         const int wfirst_key = s_wkey_first[warp];
         // my full inclusive value: add the previous warps' chain when it reaches me
-        V sfull = sc + ((wfirst_key == key && wprev_key == key) ? wprev : V(0));
+        const V sfull = sc + ((wfirst_key == key && wprev_key == key) ? wprev : V(0));
         V carry_in = __shfl_up_sync(0xffffffffu, sfull, 1);
         if (lane == 0) carry_in = wprev;
         if (tid == 0) carry_in = 0;   // the CTA carry already seeded thread 0's accumulator
-        if (first_row >= 0) {
-            const V vfirst = first_acc + carry_in;
-            if (y_in_smem) s_y[first_row] = vfirst;
-            else a.y[x0 + first_row] = vfirst;
+        if (r > r_start) {            // this thread completed row r_start: it owns that entry
+            if (y_in_smem) s_y[r_start] += carry_in;
+            else a.y[x0 + r_start] += carry_in;
         }
         if (tid == kThreads - 1) {
             s_carry = sfull;          // tile carry-out (row hi.x)
