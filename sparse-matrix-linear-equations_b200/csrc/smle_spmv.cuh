@@ -118,21 +118,23 @@ struct SpmvSmem {
     static constexpr int YBUF_ROWS = (COL_WORDS * 4) / (int)sizeof(V);
 };
 
+// longest in-tile row segment for which the thread-per-row reduction of phase B is used
+constexpr int kRowPathMaxLen = 32;
+
 template <typename V, int IPT, int STAGES, bool DOT>
 __global__ void __launch_bounds__(kThreads)
 spmv_kernel(SpmvArgs<V> a, CgScalars cg)
 {
     using SM = SpmvSmem<V, IPT>;
-    constexpr int TILE = SM::TILE;
     constexpr int EPV = SM::EPV;
 
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ uint64_t s_full[STAGES];
     __shared__ int s_wkey_first[kWarps], s_wkey_last[kWarps];
     __shared__ V s_wsum[kWarps];
-    __shared__ V s_carry;
+    __shared__ V s_carry[2];                 // tile carry, double-buffered by tile parity
+    __shared__ int s_maxlen[2];              // longest row segment of the tile, by tile parity
     __shared__ V s_red[kThreads];
-    __shared__ int s_rstart[kThreads + 1];   // rows consumed before each thread's diagonal
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
@@ -175,7 +177,8 @@ spmv_kernel(SpmvArgs<V> a, CgScalars cg)
     if (tid == 0) {
         for (int s = 0; s < STAGES; ++s) mbar_init(&s_full[s], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        s_carry = 0;
+        s_carry[0] = 0; s_carry[1] = 0;
+        s_maxlen[0] = 0; s_maxlen[1] = 0;
     }
     __syncthreads();
     if (tid == 0) {
@@ -183,11 +186,9 @@ spmv_kernel(SpmvArgs<V> a, CgScalars cg)
     }
 
     V dot = 0;
-    V carry_out = 0;
-    int last_key = a.m;
 
     for (int t = t0; t < t1; ++t) {
-        const int it = t - t0, s = it % STAGES;
+        const int it = t - t0, s = it % STAGES, par = it & 1;
         const uint32_t parity = (uint32_t)(it / STAGES) & 1u;
         const int2 lo = a.tile_xy[t], hi = a.tile_xy[t + 1];
         const int x0 = lo.x, y0 = lo.y;
@@ -195,9 +196,8 @@ spmv_kernel(SpmvArgs<V> a, CgScalars cg)
         const int yc = y0 & ~3, yv = y0 & ~(EPV - 1), rb = (x0 + 1) & ~3;
         int *s_col = stage_col(s);
         V *s_val = stage_val(s);
-        const int *s_ro = stage_ro(s);
-        V *s_y = reinterpret_cast<V *>(s_col);        // row buffer, valid after phase A
-        const bool y_in_smem = rows <= SM::YBUF_ROWS;
+        const int *s_re = stage_ro(s) + (x0 + 1 - rb);   // s_re[i] = end offset of local row i
+        const int voff = y0 - yv;                          // s_val index of the tile's first nonzero
 
         mbar_wait(&s_full[s], parity);
 
@@ -230,17 +230,16 @@ spmv_kernel(SpmvArgs<V> a, CgScalars cg)
                     for (int e = 0; e < EPV; ++e) xv[q][e] = __ldg(a.x + c[e]);
                 }
             }
-            // while the gathers fly: scatter the row-end markers to the threads that start
-            // behind them.  Marker of local row i sits at merge position pos_i = nnz_before + i;
-            // thread t (diagonal t*IPT) has consumed r_t = #{i : pos_i < t*IPT} rows.  This
-            // equals MergePathSearch(t*IPT) of the reference without a per-thread bisection.
+            // while the gathers fly: longest row segment inside this tile (complete rows, the
+            // leading part of row x0 and the trailing part of row hi.x) picks phase B's strategy
+            int mymax = 0;
             for (int i = tid; i <= rows; i += kThreads) {
-                const int prev = (i == 0) ? -1 : (s_ro[x0 + i - rb] - y0) + (i - 1);
-                const int pos = (i == rows) ? (kThreads * IPT + IPT) : (s_ro[x0 + i + 1 - rb] - y0) + i;
-                int tlo = (prev + IPT) / IPT;
-                int thi = min(pos / IPT, kThreads);
-                for (int tt = tlo; tt <= thi; ++tt) s_rstart[tt] = i;
+                const int beg = (i == 0) ? 0 : s_re[i - 1] - y0;
+                const int end = (i == rows) ? nz : s_re[i] - y0;
+                mymax = max(mymax, end - beg);
             }
+            mymax = __reduce_max_sync(0xffffffffu, mymax);
+            if (lane == 0 && mymax > 0) atomicMax(&s_maxlen[par], mymax);
 #pragma unroll
             for (int q = 0; q < MAXIT; ++q) {
                 const int g = tid + q * kThreads;
@@ -253,95 +252,121 @@ spmv_kernel(SpmvArgs<V> a, CgScalars cg)
         }
         __syncthreads();
 
-        // ---- phase B: per-thread merge walk over IPT items (predicated, no divergence) ----------
-        const int d0 = min(tid * IPT, items);
-        const int r_start = min(s_rstart[tid], rows);
-        int r = r_start;
-        int z = d0 - r;
-        const int voff = y0 - yv;
-        V acc = (tid == 0) ? s_carry : V(0);
-        int cur_end = s_ro[x0 + r + 1 - rb] - y0;
-        const int n_items = min(IPT, items - d0);
-#pragma unroll
-        for (int i = 0; i < IPT; ++i) {
-            const bool live = i < n_items;
-            const bool is_nz = live && (z < cur_end);
-            const V pv = s_val[voff + z];             // always in bounds of the stage buffer
-            if (is_nz) { acc += pv; ++z; }
-            if (live && !is_nz) {
-                if (y_in_smem) s_y[r] = acc; else a.y[x0 + r] = acc;
-                acc = 0;
-                ++r;
-                cur_end = s_ro[x0 + r + 1 - rb] - y0;
-            }
-        }
-
-        // ---- carries: inclusive segmented scan keyed by the row in progress ----------------------
-        const int key = x0 + r;
-        V sc = acc;
-        {
-            const int pkey = __shfl_up_sync(0xffffffffu, key, 1);
-            const bool same = lane > 0 && pkey == key;
-            if (__any_sync(0xffffffffu, same)) {   // some row spans several threads of this warp
-#pragma unroll
-                for (int d = 1; d < 32; d <<= 1) {
-                    const int okey = __shfl_up_sync(0xffffffffu, key, d);
-                    const V o = __shfl_up_sync(0xffffffffu, sc, d);
-                    if (lane >= d && okey == key) sc += o;
+        if (s_maxlen[par] <= kRowPathMaxLen) {
+            // ---- phase B, regular tile: one thread per row, coalesced y, no scan ----------------
+            // (pseudo-row `rows` is the trailing part of row hi.x: its sum is the tile carry-out)
+            for (int i = tid; i <= rows; i += kThreads) {
+                const int beg = (i == 0) ? 0 : s_re[i - 1] - y0;
+                const int end = (i == rows) ? nz : s_re[i] - y0;
+                V sum = (i == 0) ? s_carry[par] : V(0);
+                const V *pv = s_val + voff;
+                for (int z = beg; z < end; ++z) sum += pv[z];
+                if (i < rows) {
+                    a.y[x0 + i] = sum;
+                    if constexpr (DOT) dot += sum * __ldg(a.x + x0 + i);
+                } else {
+                    s_carry[par ^ 1] = sum;
                 }
             }
-        }
-        if (lane == 31) { s_wkey_last[warp] = key; s_wsum[warp] = sc; }
-        if (lane == 0) s_wkey_first[warp] = key;
-        __syncthreads();
-        // full inclusive value of the previous warps' last threads (a row may chain across warps)
-        V wprev = 0;
-        for (int wi = 0; wi < warp; ++wi) {
-            const bool chain = wi > 0 && s_wkey_first[wi] == s_wkey_last[wi] &&
-                               s_wkey_last[wi - 1] == s_wkey_last[wi];
-            wprev = s_wsum[wi] + (chain ? wprev : V(0));
-        }
-        const int wprev_key = warp > 0 ? s_wkey_last[warp - 1] : -1;
-        const int wfirst_key = s_wkey_first[warp];
-        // my full inclusive value: add the previous warps' chain when it reaches me
-        const V sfull = sc + ((wfirst_key == key && wprev_key == key) ? wprev : V(0));
-        V carry_in = __shfl_up_sync(0xffffffffu, sfull, 1);
-        if (lane == 0) carry_in = wprev;
-        if (tid == 0) carry_in = 0;   // the CTA carry already seeded thread 0's accumulator
-        if (r > r_start) {            // this thread completed row r_start: it owns that entry
-            if (y_in_smem) s_y[r_start] += carry_in;
-            else a.y[x0 + r_start] += carry_in;
-        }
-        if (tid == kThreads - 1) {
-            s_carry = sfull;          // tile carry-out (row hi.x)
-            carry_out = sfull;
-            last_key = key;
-        }
-        __syncthreads();
-
-        // ---- phase C: coalesced row output (+ dot) -----------------------------------------------
-        if (y_in_smem) {
-            for (int i = tid; i < rows; i += kThreads) {
-                const V v = s_y[i];
-                a.y[x0 + i] = v;
-                if constexpr (DOT) dot += v * __ldg(a.x + x0 + i);
+        } else {
+            // ---- phase B, general tile: merge-path walk, IPT items per thread ---------------------
+            V *s_y = reinterpret_cast<V *>(s_col);        // row buffer (columns are consumed)
+            const bool y_in_smem = rows <= SM::YBUF_ROWS;
+            const int d0 = min(tid * IPT, items);
+            int r_start;
+            {
+                // MergePathSearch (merge_based.hpp:22-44) on the staged row-end offsets
+                int l = max(d0 - nz, 0), h = min(d0, rows);
+                while (l < h) {
+                    const int mid = (l + h) >> 1;
+                    if (s_re[mid] - y0 <= d0 - mid - 1) l = mid + 1; else h = mid;
+                }
+                r_start = l;
             }
-        } else if constexpr (DOT) {
-            __threadfence_block();
-            for (int i = tid; i < rows; i += kThreads) dot += a.y[x0 + i] * __ldg(a.x + x0 + i);
-        }
-        __syncthreads();   // stage s fully consumed
+            int r = r_start;
+            int z = d0 - r;
+            V acc = (tid == 0) ? s_carry[par] : V(0);
+            int cur_end = s_re[r] - y0;
+            const int n_items = min(IPT, items - d0);
+#pragma unroll
+            for (int i = 0; i < IPT; ++i) {
+                const bool live = i < n_items;
+                const bool is_nz = live && (z < cur_end);
+                const V pv = s_val[voff + z];             // always inside the stage buffer
+                if (is_nz) { acc += pv; ++z; }
+                if (live && !is_nz) {
+                    if (y_in_smem) s_y[r] = acc; else a.y[x0 + r] = acc;
+                    acc = 0;
+                    ++r;
+                    cur_end = s_re[r] - y0;
+                }
+            }
 
-        if (tid == 0 && t + STAGES < t1) {
-            fence_proxy_async();
-            issue(t + STAGES, s);
+            // carries: inclusive segmented scan keyed by the row in progress
+            const int key = x0 + r;
+            V sc = acc;
+            {
+                const int pkey = __shfl_up_sync(0xffffffffu, key, 1);
+                const bool same = lane > 0 && pkey == key;
+                if (__any_sync(0xffffffffu, same)) {   // a row spans several threads of this warp
+#pragma unroll
+                    for (int d = 1; d < 32; d <<= 1) {
+                        const int okey = __shfl_up_sync(0xffffffffu, key, d);
+                        const V o = __shfl_up_sync(0xffffffffu, sc, d);
+                        if (lane >= d && okey == key) sc += o;
+                    }
+                }
+            }
+            if (lane == 31) { s_wkey_last[warp] = key; s_wsum[warp] = sc; }
+            if (lane == 0) s_wkey_first[warp] = key;
+            __syncthreads();
+            // full inclusive value of the previous warps' last threads (rows may chain across warps)
+            V wprev = 0;
+            for (int wi = 0; wi < warp; ++wi) {
+                const bool chain = wi > 0 && s_wkey_first[wi] == s_wkey_last[wi] &&
+                                   s_wkey_last[wi - 1] == s_wkey_last[wi];
+                wprev = s_wsum[wi] + (chain ? wprev : V(0));
+            }
+            const int wprev_key = warp > 0 ? s_wkey_last[warp - 1] : -1;
+            const int wfirst_key = s_wkey_first[warp];
+            const V sfull = sc + ((wfirst_key == key && wprev_key == key) ? wprev : V(0));
+            V carry_in = __shfl_up_sync(0xffffffffu, sfull, 1);
+            if (lane == 0) carry_in = wprev;
+            if (tid == 0) carry_in = 0;   // the tile carry already seeded thread 0's accumulator
+            if (r > r_start) {            // this thread completed row r_start: it owns that entry
+                if (y_in_smem) s_y[r_start] += carry_in;
+                else a.y[x0 + r_start] += carry_in;
+            }
+            if (tid == kThreads - 1) s_carry[par ^ 1] = sfull;   // tile carry-out (row hi.x)
+            __syncthreads();
+
+            // phase C: coalesced row output (+ dot)
+            if (y_in_smem) {
+                for (int i = tid; i < rows; i += kThreads) {
+                    const V v = s_y[i];
+                    a.y[x0 + i] = v;
+                    if constexpr (DOT) dot += v * __ldg(a.x + x0 + i);
+                }
+            } else if constexpr (DOT) {
+                for (int i = tid; i < rows; i += kThreads) dot += a.y[x0 + i] * __ldg(a.x + x0 + i);
+            }
+        }
+        __syncthreads();   // stage s fully consumed, s_carry[par^1] published
+
+        if (tid == 0) {
+            s_maxlen[par] = 0;
+            if (t + STAGES < t1) {
+                fence_proxy_async();
+                issue(t + STAGES, s);
+            }
         }
     }
 
     // ---- CTA carry-out ---------------------------------------------------------------------------
-    if (tid == kThreads - 1) {
-        a.carry_row[blockIdx.x] = (t1 > t0) ? last_key : a.m;
-        a.carry_val[blockIdx.x] = (t1 > t0) ? carry_out : V(0);
+    if (tid == 0) {
+        const bool any = t1 > t0;
+        a.carry_row[blockIdx.x] = any ? a.tile_xy[t1].x : a.m;
+        a.carry_val[blockIdx.x] = any ? s_carry[(t1 - t0) & 1] : V(0);
     }
 
     if constexpr (DOT) {
