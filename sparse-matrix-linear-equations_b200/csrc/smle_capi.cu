@@ -90,6 +90,7 @@ struct Partition {
     int items_per_tile = 0;
     int num_tiles = 0;
     int2 *xy = nullptr;   // device, num_tiles + 1
+    int *maxlen = nullptr; // device, num_tiles: longest in-tile row segment
 };
 
 struct smle_csr_s {
@@ -135,6 +136,11 @@ int get_partition(smle_csr_t a, int items_per_tile, Partition **out)
                                                          p.num_tiles, p.xy);
     ++g_launches;
     int rc = check_launch("merge_partition_kernel");
+    if (rc) return rc;
+    CU(cudaMalloc(&p.maxlen, sizeof(int) * (size_t)p.num_tiles));
+    tile_maxlen_kernel<<<(p.num_tiles * 32 + 255) / 256, 256, 0, g_stream>>>(a->ro, p.xy, p.num_tiles, p.maxlen);
+    ++g_launches;
+    rc = check_launch("tile_maxlen_kernel");
     if (rc) return rc;
     a->parts[items_per_tile] = p;
     *out = &a->parts[items_per_tile];
@@ -253,7 +259,7 @@ int launch_spmv(smle_csr_t a, const V *x, V *y, const CgScalars &cg, bool dry)
     grid = (p->num_tiles + tiles_per_cta - 1) / tiles_per_cta;
     SpmvArgs<V> args;
     args.ro = a->ro; args.ci = a->ci; args.va = (const V *)a->va;
-    args.x = x; args.y = y; args.tile_xy = p->xy;
+    args.x = x; args.y = y; args.tile_xy = p->xy; args.tile_maxlen = p->maxlen;
     args.m = a->m; args.nnz = a->nnz;
     args.num_tiles = p->num_tiles; args.tiles_per_cta = tiles_per_cta;
     args.carry_row = a->carry_row; args.carry_val = (V *)a->carry_val;
@@ -659,7 +665,7 @@ void smle_csr_destroy(smle_csr_t a)
     if (!a) return;
     if (g_stream) cudaStreamSynchronize(g_stream);
     free_workspace(a->ws);
-    for (auto &kv : a->parts) cudaFree(kv.second.xy);
+    for (auto &kv : a->parts) { cudaFree(kv.second.xy); cudaFree(kv.second.maxlen); }
     cudaFree(a->ro); cudaFree(a->ci); cudaFree(a->va);
     cudaFree(a->carry_row); cudaFree(a->carry_val); cudaFree(a->dot_part); cudaFree(a->fix_part);
     cudaFree(a->ticket);

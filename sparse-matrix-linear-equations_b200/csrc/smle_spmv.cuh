@@ -96,6 +96,7 @@ struct SpmvArgs {
     const V *__restrict__ x;
     V *__restrict__ y;
     const int2 *__restrict__ tile_xy;  // num_tiles + 1 merge-path coordinates
+    const int *__restrict__ tile_maxlen;  // longest in-tile row segment per tile (matrix property)
     int m, nnz;
     int num_tiles, tiles_per_cta;
     int *carry_row;                    // [gridDim.x]
@@ -118,8 +119,28 @@ struct SpmvSmem {
     static constexpr int YBUF_ROWS = (COL_WORDS * 4) / (int)sizeof(V);
 };
 
-// longest in-tile row segment for which the thread-per-row reduction of phase B is used
+// longest in-tile row segment for which the fused thread-per-row path is used
 constexpr int kRowPathMaxLen = 32;
+
+// One warp per tile: the longest run of nonzeros of a single row inside the tile (complete rows,
+// the leading part of row x0 and the trailing part of row x1).  A property of the matrix and the
+// tiling only, computed once per handle next to the merge-path coordinates.
+__global__ void tile_maxlen_kernel(const int *__restrict__ ro, const int2 *__restrict__ tile_xy, int num_tiles,
+                                   int *__restrict__ out)
+{
+    const int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (t >= num_tiles) return;
+    const int2 lo = tile_xy[t], hi = tile_xy[t + 1];
+    const int rows = hi.x - lo.x;
+    int mx = 0;
+    for (int i = lane; i <= rows; i += 32) {
+        const int beg = (i == 0) ? lo.y : __ldg(ro + lo.x + i);          // end of the previous row
+        const int end = (i == rows) ? hi.y : __ldg(ro + lo.x + i + 1);
+        mx = max(mx, end - beg);
+    }
+    mx = __reduce_max_sync(0xffffffffu, mx);
+    if (lane == 0) out[t] = mx;
+}
 
 template <typename V, int IPT, int STAGES, bool DOT>
 __global__ void __launch_bounds__(kThreads)
@@ -133,7 +154,6 @@ spmv_kernel(SpmvArgs<V> a, CgScalars cg)
     __shared__ int s_wkey_first[kWarps], s_wkey_last[kWarps];
     __shared__ V s_wsum[kWarps];
     __shared__ V s_carry[2];                 // tile carry, double-buffered by tile parity
-    __shared__ int s_maxlen[2];              // longest row segment of the tile, by tile parity
     __shared__ V s_red[kThreads];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -178,7 +198,6 @@ spmv_kernel(SpmvArgs<V> a, CgScalars cg)
         for (int s = 0; s < STAGES; ++s) mbar_init(&s_full[s], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         s_carry[0] = 0; s_carry[1] = 0;
-        s_maxlen[0] = 0; s_maxlen[1] = 0;
     }
     __syncthreads();
     if (tid == 0) {
@@ -201,75 +220,108 @@ spmv_kernel(SpmvArgs<V> a, CgScalars cg)
 
         mbar_wait(&s_full[s], parity);
 
-        // ---- phase A: products in place ------------------------------------------------------
-        // all shared loads and all gathers of a thread are issued before the first product is
-        // written back, so MAXIT*EPV independent global loads are in flight per thread.  The
-        // 16-byte groups at the edges may include nonzeros of the neighbouring tiles: their
-        // products are computed (the column is valid; the slack behind ci is zero-filled) and
-        // never read.
-        {
-            const int nvec = (hi.y - yv + EPV - 1) / EPV;   // 16-byte groups staged
-            constexpr int MAXIT = (SM::VAL_ELEMS / EPV + kThreads - 1) / kThreads;
-            V v[MAXIT][EPV];
-            V xv[MAXIT][EPV];
-            const int cshift = yv - yc;                     // s_col index of value group 0
+        if (a.tile_maxlen[t] <= kRowPathMaxLen) {
+            // ---- regular tile: fused thread-per-row path -------------------------------------------
+            // Thread i owns local row i (and i+256, interleaved for ILP): it reads the row's values
+            // and columns from the stage buffers, gathers x (adjacent lanes = adjacent rows, so the
+            // gathers coalesce for banded matrices), and writes y[row] directly -- coalesced, no
+            // product staging, no scan.  Pseudo-row `rows` is the trailing part of row hi.x: its sum
+            // is the tile carry-out; row 0 starts from the carry-in.
+            const int *pc = s_col + (y0 - yc);
+            const V *pvv = s_val + voff;
+            for (int i = tid; i <= rows; i += 2 * kThreads) {
+                const int iB = i + kThreads;
+                const bool hasB = iB <= rows;
+                int begA = (i == 0) ? 0 : s_re[i - 1] - y0;
+                const int endA = (i == rows) ? nz : s_re[i] - y0;
+                int begB = 0, endB = 0;
+                if (hasB) {
+                    begB = s_re[iB - 1] - y0;
+                    endB = (iB == rows) ? nz : s_re[iB] - y0;
+                }
+                V xrA = 0, xrB = 0;
+                if constexpr (DOT) {
+                    if (i < rows) xrA = __ldg(a.x + x0 + i);
+                    if (hasB && iB < rows) xrB = __ldg(a.x + x0 + iB);
+                }
+                V sumA = (i == 0) ? s_carry[par] : V(0), sumB = 0;
+                while (begA < endA || begB < endB) {
+                    constexpr int UB = 8;
+                    V va[UB], xa[UB], vb[UB], xb[UB];
 #pragma unroll
-            for (int q = 0; q < MAXIT; ++q) {
-                const int g = tid + q * kThreads;           // group index
-                if (g < nvec) {
-                    int c[EPV];
-                    ld_vec<V, EPV>(v[q], s_val + g * EPV);
-                    if constexpr (EPV == 2) {
-                        int2 cc = *reinterpret_cast<const int2 *>(s_col + cshift + g * EPV);
-                        c[0] = cc.x; c[1] = cc.y;
-                    } else {
-                        int4 cc = *reinterpret_cast<const int4 *>(s_col + cshift + g * EPV);
-                        c[0] = cc.x; c[1] = cc.y; c[2] = cc.z; c[3] = cc.w;
+                    for (int j = 0; j < UB; ++j) {
+                        va[j] = 0; xa[j] = 0;
+                        if (begA + j < endA) { va[j] = pvv[begA + j]; xa[j] = __ldg(a.x + pc[begA + j]); }
                     }
 #pragma unroll
-                    for (int e = 0; e < EPV; ++e) xv[q][e] = __ldg(a.x + c[e]);
-                }
-            }
-            // while the gathers fly: longest row segment inside this tile (complete rows, the
-            // leading part of row x0 and the trailing part of row hi.x) picks phase B's strategy
-            int mymax = 0;
-            for (int i = tid; i <= rows; i += kThreads) {
-                const int beg = (i == 0) ? 0 : s_re[i - 1] - y0;
-                const int end = (i == rows) ? nz : s_re[i] - y0;
-                mymax = max(mymax, end - beg);
-            }
-            mymax = __reduce_max_sync(0xffffffffu, mymax);
-            if (lane == 0 && mymax > 0) atomicMax(&s_maxlen[par], mymax);
+                    for (int j = 0; j < UB; ++j) {
+                        vb[j] = 0; xb[j] = 0;
+                        if (begB + j < endB) { vb[j] = pvv[begB + j]; xb[j] = __ldg(a.x + pc[begB + j]); }
+                    }
 #pragma unroll
-            for (int q = 0; q < MAXIT; ++q) {
-                const int g = tid + q * kThreads;
-                if (g < nvec) {
+                    for (int j = 0; j < UB; ++j) sumA += va[j] * xa[j];
 #pragma unroll
-                    for (int e = 0; e < EPV; ++e) v[q][e] *= xv[q][e];
-                    st_vec<V, EPV>(s_val + g * EPV, v[q]);
+                    for (int j = 0; j < UB; ++j) sumB += vb[j] * xb[j];
+                    begA += UB; begB += UB;
                 }
-            }
-        }
-        __syncthreads();
-
-        if (s_maxlen[par] <= kRowPathMaxLen) {
-            // ---- phase B, regular tile: one thread per row, coalesced y, no scan ----------------
-            // (pseudo-row `rows` is the trailing part of row hi.x: its sum is the tile carry-out)
-            for (int i = tid; i <= rows; i += kThreads) {
-                const int beg = (i == 0) ? 0 : s_re[i - 1] - y0;
-                const int end = (i == rows) ? nz : s_re[i] - y0;
-                V sum = (i == 0) ? s_carry[par] : V(0);
-                const V *pv = s_val + voff;
-                for (int z = beg; z < end; ++z) sum += pv[z];
                 if (i < rows) {
-                    a.y[x0 + i] = sum;
-                    if constexpr (DOT) dot += sum * __ldg(a.x + x0 + i);
+                    a.y[x0 + i] = sumA;
+                    if constexpr (DOT) dot += sumA * xrA;
                 } else {
-                    s_carry[par ^ 1] = sum;
+                    s_carry[par ^ 1] = sumA;
+                }
+                if (hasB) {
+                    if (iB < rows) {
+                        a.y[x0 + iB] = sumB;
+                        if constexpr (DOT) dot += sumB * xrB;
+                    } else {
+                        s_carry[par ^ 1] = sumB;
+                    }
                 }
             }
         } else {
-            // ---- phase B, general tile: merge-path walk, IPT items per thread ---------------------
+            // ---- general tile, phase A: products in place -------------------------------------------
+            // all shared loads and all gathers of a thread are issued before the first product is
+            // written back, so MAXIT*EPV independent global loads are in flight per thread.  The
+            // 16-byte groups at the edges may include nonzeros of the neighbouring tiles: their
+            // products are computed (the column is valid; the slack behind ci is zero-filled) and
+            // never read.
+            {
+                const int nvec = (hi.y - yv + EPV - 1) / EPV;   // 16-byte groups staged
+                constexpr int MAXIT = (SM::VAL_ELEMS / EPV + kThreads - 1) / kThreads;
+                V v[MAXIT][EPV];
+                V xv[MAXIT][EPV];
+                const int cshift = yv - yc;                     // s_col index of value group 0
+#pragma unroll
+                for (int q = 0; q < MAXIT; ++q) {
+                    const int g = tid + q * kThreads;           // group index
+                    if (g < nvec) {
+                        int c[EPV];
+                        ld_vec<V, EPV>(v[q], s_val + g * EPV);
+                        if constexpr (EPV == 2) {
+                            int2 cc = *reinterpret_cast<const int2 *>(s_col + cshift + g * EPV);
+                            c[0] = cc.x; c[1] = cc.y;
+                        } else {
+                            int4 cc = *reinterpret_cast<const int4 *>(s_col + cshift + g * EPV);
+                            c[0] = cc.x; c[1] = cc.y; c[2] = cc.z; c[3] = cc.w;
+                        }
+#pragma unroll
+                        for (int e = 0; e < EPV; ++e) xv[q][e] = __ldg(a.x + c[e]);
+                    }
+                }
+#pragma unroll
+                for (int q = 0; q < MAXIT; ++q) {
+                    const int g = tid + q * kThreads;
+                    if (g < nvec) {
+#pragma unroll
+                        for (int e = 0; e < EPV; ++e) v[q][e] *= xv[q][e];
+                        st_vec<V, EPV>(s_val + g * EPV, v[q]);
+                    }
+                }
+            }
+            __syncthreads();
+
+            // ---- general tile, phase B: merge-path walk, IPT items per thread ------------------------
             V *s_y = reinterpret_cast<V *>(s_col);        // row buffer (columns are consumed)
             const bool y_in_smem = rows <= SM::YBUF_ROWS;
             const int d0 = min(tid * IPT, items);
@@ -353,12 +405,9 @@ spmv_kernel(SpmvArgs<V> a, CgScalars cg)
         }
         __syncthreads();   // stage s fully consumed, s_carry[par^1] published
 
-        if (tid == 0) {
-            s_maxlen[par] = 0;
-            if (t + STAGES < t1) {
-                fence_proxy_async();
-                issue(t + STAGES, s);
-            }
+        if (tid == 0 && t + STAGES < t1) {
+            fence_proxy_async();
+            issue(t + STAGES, s);
         }
     }
 
