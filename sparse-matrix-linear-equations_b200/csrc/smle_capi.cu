@@ -230,15 +230,15 @@ int launch_merge_t(smle_csr_t a, const V *X, V *Y, int k, const CgScalars &cg, b
 }
 
 // k == 1: the TMA-staged single-vector kernel (smle_spmv.cuh)
-constexpr int kSpmvIPT = 12;      // merge items per thread per tile
-constexpr int kSpmvStages = 2;    // tiles in flight per CTA
-
-template <typename V, bool DOT>
-int launch_spmv(smle_csr_t a, const V *x, V *y, const CgScalars &cg, bool dry)
+//   IPT    merge items per thread per tile (tile = 256*IPT items)
+//   STAGES tiles in flight per CTA
+// The default was picked from the sweep in profiles/ (SMLE_SPMV_CFG=<ipt>x<stages> overrides it).
+template <typename V, int IPT, int STAGES, bool DOT>
+int launch_spmv_t(smle_csr_t a, const V *x, V *y, const CgScalars &cg, bool dry)
 {
-    using SM = SpmvSmem<V, kSpmvIPT>;
-    constexpr size_t smem = SM::STAGE_BYTES * kSpmvStages;
-    auto kern = spmv_kernel<V, kSpmvIPT, kSpmvStages, DOT>;
+    using SM = SpmvSmem<V, IPT>;
+    constexpr size_t smem = SM::STAGE_BYTES * STAGES;
+    auto kern = spmv_kernel<V, IPT, STAGES, DOT>;
     Partition *p;
     int rc = get_partition(a, SM::TILE, &p);
     if (rc) return rc;
@@ -268,6 +268,33 @@ int launch_spmv(smle_csr_t a, const V *x, V *y, const CgScalars &cg, bool dry)
     kern<<<grid, kThreads, smem, g_stream>>>(args, cg);
     ++g_launches;
     return check_launch("spmv_kernel");
+}
+
+constexpr int kSpmvIPT = 12, kSpmvStages = 2;   // default configuration
+
+int spmv_cfg()
+{
+    static int cfg = -1;
+    if (cfg < 0) {
+        cfg = kSpmvIPT * 10 + kSpmvStages;
+        const char *e = getenv("SMLE_SPMV_CFG");
+        int i = 0, st = 0;
+        if (e && sscanf(e, "%dx%d", &i, &st) == 2) cfg = i * 10 + st;
+    }
+    return cfg;
+}
+
+int spmv_tile_items() { return kThreads * (spmv_cfg() / 10); }
+
+template <typename V, bool DOT>
+int launch_spmv(smle_csr_t a, const V *x, V *y, const CgScalars &cg, bool dry)
+{
+    switch (spmv_cfg()) {
+#define SMLE_CFG(i, st) case i * 10 + st: return launch_spmv_t<V, i, st, DOT>(a, x, y, cg, dry);
+        SMLE_CFG(12, 2) SMLE_CFG(8, 2) SMLE_CFG(8, 3) SMLE_CFG(6, 2) SMLE_CFG(6, 3) SMLE_CFG(16, 2) SMLE_CFG(12, 3)
+#undef SMLE_CFG
+    }
+    return fail(SMLE_ERR_ARG, "unsupported SMLE_SPMV_CFG");
 }
 
 template <typename V, bool DOT>
@@ -413,6 +440,16 @@ int launch_vec_t(int which, const CgVecArgs &va, const CgScalars &cg, int max_it
 
 int launch_vec(int which, const CgVecArgs &va, const CgScalars &cg, int max_iters = 0, double tol = 0.0)
 {
+    if (va.k == 1 && which != 0 && getenv("SMLE_VEC_GENERIC") == nullptr) {
+        // single right-hand side: 128-bit, unrolled kernels with L2 eviction priorities
+        long long want = ((long long)(va.n >> 1) + kThreads * kVecUnroll - 1) / (kThreads * kVecUnroll);
+        int grid = (int)(want < (long long)g_sms * 8 ? want : (long long)g_sms * 8);
+        if (grid < 1) grid = 1;
+        if (which == 1) cg1_update_r_kernel<<<grid, kThreads, 0, g_stream>>>(va, cg);
+        else cg1_update_xp_kernel<<<grid, kThreads, 0, g_stream>>>(va, cg);
+        ++g_launches;
+        return check_launch("cg1 vector kernel");
+    }
     int G, VEC;
     pick_shape<double>(va.k, &G, &VEC);
     const int W = kThreads / G;
@@ -688,7 +725,7 @@ int smle_csr_tile_coords(smle_csr_t a, int k, int *num_tiles, int *items_per_til
     int rc = ensure_init();
     if (rc) return rc;
     Partition *p;
-    rc = get_partition(a, k == 1 ? kThreads * kSpmvIPT : kTileItems, &p);
+    rc = get_partition(a, k == 1 ? spmv_tile_items() : kTileItems, &p);
     if (rc) return rc;
     if (num_tiles) *num_tiles = p->num_tiles;
     if (items_per_tile) *items_per_tile = p->items_per_tile;

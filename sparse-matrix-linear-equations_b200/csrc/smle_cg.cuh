@@ -113,6 +113,49 @@ cg_init_kernel(CgVecArgs a, CgScalars cg, int max_iters, double tol)
 }
 
 // ---------------------------------------------------------------------------------------
+// Epilogue of K2, run by the last CTA to finish: rs_new from the per-CTA partials, per-column
+// relative residual and latch (no_pretreatment.hpp:133-155), beta (:165-176), rs_old <- rs_new
+// (:179-181), error history, iteration count, stop flag (:157-161 or max_iters).
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ void cg_finalize_r(const CgVecArgs &a, const CgScalars &cg, double *s_red, int *s_cnt)
+{
+    const int tid = threadIdx.x;
+    cta_reduce_columns<double>(a.part, nullptr, gridDim.x, a.k, cg.rs_new, s_red);
+
+    double worst = 0.0;
+    int nconv = 0;
+    const double tol = *cg.tol;
+    for (int c = tid; c < a.k; c += kThreads) {
+        const double rn = cg.rs_new[c], ro = cg.rs_old[c];
+        const double rel = sqrt(rn) / cg.bnorm[c];
+        worst = fmax(worst, rel);
+        int cv = cg.conv[c];
+        if (!cv && rel < tol) { cv = 1; cg.conv[c] = 1; }
+        nconv += cv;
+        cg.beta[c] = cv ? 0.0 : rn / ro;
+        cg.rs_old[c] = rn;
+    }
+    s_red[tid] = worst;
+    s_cnt[tid] = nconv;
+    __syncthreads();
+    for (int d = kThreads / 2; d > 0; d >>= 1) {
+        if (tid < d) {
+            s_red[tid] = fmax(s_red[tid], s_red[tid + d]);
+            s_cnt[tid] += s_cnt[tid + d];
+        }
+        __syncthreads();
+    }
+    if (tid == 0) {
+        const int it = cg.ctrl[CTRL_ITER];
+        if (cg.hist && it < cg.hist_cap) cg.hist[it] = s_red[0];
+        *cg.last_rel = s_red[0];
+        cg.ctrl[CTRL_ITER] = it + 1;
+        cg.ctrl[CTRL_NCONV] = s_cnt[0];
+        if (s_cnt[0] == a.k || it + 1 >= cg.ctrl[CTRL_MAX_ITERS]) cg.ctrl[CTRL_STOP] = 1;
+    }
+}
+
+// ---------------------------------------------------------------------------------------
 // K2: R -= alpha * AP and r.r  (no_pretreatment.hpp:125-130; single_strategy.hpp:147-149).
 // Last CTA: rs_new, per-column relative residual and latch (:133-155), beta (:165-176),
 // rs_old <- rs_new (:179-181), history, iteration count, stop flag (:157-161 or max_iters).
@@ -152,39 +195,7 @@ cg_update_r_kernel(CgVecArgs a, CgScalars cg)
     }
 
     if (!last_cta_election(a.ticket, gridDim.x)) return;
-    cta_reduce_columns<double>(a.part, nullptr, gridDim.x, a.k, cg.rs_new, s_red);
-
-    double worst = 0.0;
-    int nconv = 0;
-    const double tol = *cg.tol;
-    for (int c = tid; c < a.k; c += kThreads) {
-        const double rn = cg.rs_new[c], ro = cg.rs_old[c];
-        const double rel = sqrt(rn) / cg.bnorm[c];
-        worst = fmax(worst, rel);
-        int cv = cg.conv[c];
-        if (!cv && rel < tol) { cv = 1; cg.conv[c] = 1; }
-        nconv += cv;
-        cg.beta[c] = cv ? 0.0 : rn / ro;
-        cg.rs_old[c] = rn;
-    }
-    s_red[tid] = worst;
-    s_cnt[tid] = nconv;
-    __syncthreads();
-    for (int d = kThreads / 2; d > 0; d >>= 1) {
-        if (tid < d) {
-            s_red[tid] = fmax(s_red[tid], s_red[tid + d]);
-            s_cnt[tid] += s_cnt[tid + d];
-        }
-        __syncthreads();
-    }
-    if (tid == 0) {
-        const int it = cg.ctrl[CTRL_ITER];
-        if (cg.hist && it < cg.hist_cap) cg.hist[it] = s_red[0];
-        *cg.last_rel = s_red[0];
-        cg.ctrl[CTRL_ITER] = it + 1;
-        cg.ctrl[CTRL_NCONV] = s_cnt[0];
-        if (s_cnt[0] == a.k || it + 1 >= cg.ctrl[CTRL_MAX_ITERS]) cg.ctrl[CTRL_STOP] = 1;
-    }
+    cg_finalize_r(a, cg, s_red, s_cnt);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -224,6 +235,109 @@ cg_update_xp_kernel(CgVecArgs a, CgScalars cg)
                 st_vec<double, VEC>(a.P + off, p);
             }
         }
+    }
+}
+
+// =======================================================================================
+// Single right-hand side (k = 1) specialisations of K2 / K3: 128-bit accesses, four
+// independent vectors in flight per thread, explicit L2 eviction priorities.
+// =======================================================================================
+constexpr int kVecUnroll = 4;
+
+__global__ void __launch_bounds__(kThreads)
+cg1_update_r_kernel(CgVecArgs a, CgScalars cg)
+{
+    __shared__ double s_red[kThreads];
+    __shared__ int s_cnt[kThreads];
+    if (cg.ctrl[CTRL_STOP]) return;
+    const int tid = threadIdx.x;
+    const uint64_t pol_first = make_policy_evict_first(), pol_last = make_policy_evict_last();
+    const double na = -cg.alpha[0];
+    const long long n2 = a.n >> 1;
+    const long long stride = (long long)gridDim.x * kThreads;
+    double s = 0.0;
+    for (long long i = (long long)blockIdx.x * kThreads + tid; i < n2; i += stride * kVecUnroll) {
+        double2 r[kVecUnroll], ap[kVecUnroll];
+#pragma unroll
+        for (int u = 0; u < kVecUnroll; ++u) {
+            const long long j = i + u * stride;
+            if (j < n2) {
+                r[u] = ld_f64x2_hint(a.R + 2 * j, pol_last);
+                ap[u] = ld_f64x2_hint(a.AP + 2 * j, pol_first);   // AP is dead after this read
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < kVecUnroll; ++u) {
+            const long long j = i + u * stride;
+            if (j < n2) {
+                r[u].x += na * ap[u].x;
+                r[u].y += na * ap[u].y;
+                s += r[u].x * r[u].x;
+                s += r[u].y * r[u].y;
+                st_f64x2_hint(a.R + 2 * j, r[u], pol_last);       // K3 reads r next
+            }
+        }
+    }
+    if ((a.n & 1) && blockIdx.x == 0 && tid == 0) {
+        const int j = a.n - 1;
+        double r = a.R[j] + na * a.AP[j];
+        a.R[j] = r;
+        s += r * r;
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
+    if ((tid & 31) == 0) s_red[tid >> 5] = s;
+    __syncthreads();
+    if (tid == 0) {
+        double t = 0;
+        for (int i = 0; i < kWarps; ++i) t += s_red[i];
+        a.part[blockIdx.x] = t;
+    }
+    if (!last_cta_election(a.ticket, gridDim.x)) return;
+    cg_finalize_r(a, cg, s_red, s_cnt);
+}
+
+__global__ void __launch_bounds__(kThreads)
+cg1_update_xp_kernel(CgVecArgs a, CgScalars cg)
+{
+    if (cg.ctrl[CTRL_HALT]) return;
+    const bool final_iter = cg.ctrl[CTRL_STOP] != 0;
+    const int tid = threadIdx.x;
+    const uint64_t pol_first = make_policy_evict_first(), pol_last = make_policy_evict_last();
+    const double al = cg.alpha[0], be = cg.beta[0];
+    const long long n2 = a.n >> 1;
+    const long long stride = (long long)gridDim.x * kThreads;
+    for (long long i = (long long)blockIdx.x * kThreads + tid; i < n2; i += stride * kVecUnroll) {
+        double2 x[kVecUnroll], p[kVecUnroll], r[kVecUnroll];
+#pragma unroll
+        for (int u = 0; u < kVecUnroll; ++u) {
+            const long long j = i + u * stride;
+            if (j < n2) {
+                x[u] = ld_f64x2_hint(a.X + 2 * j, pol_first);      // x is touched once per iteration
+                p[u] = ld_f64x2_hint(a.P + 2 * j, pol_last);
+                if (!final_iter) r[u] = ld_f64x2_hint(a.R + 2 * j, pol_last);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < kVecUnroll; ++u) {
+            const long long j = i + u * stride;
+            if (j < n2) {
+                x[u].x += al * p[u].x;
+                x[u].y += al * p[u].y;
+                st_f64x2_hint(a.X + 2 * j, x[u], pol_first);
+                if (!final_iter) {
+                    p[u].x = r[u].x + be * p[u].x;
+                    p[u].y = r[u].y + be * p[u].y;
+                    st_f64x2_hint(a.P + 2 * j, p[u], pol_last);    // the SpMV gathers p next
+                }
+            }
+        }
+    }
+    if ((a.n & 1) && blockIdx.x == 0 && tid == 0) {
+        const int j = a.n - 1;
+        const double pj = a.P[j];
+        a.X[j] += al * pj;
+        if (!final_iter) a.P[j] = a.R[j] + be * pj;
     }
 }
 

@@ -100,6 +100,66 @@ __device__ __forceinline__ void st_vec(V *p, const V (&in)[VEC])
 }
 
 // ---------------------------------------------------------------------------------------
+// L2 residency control.  B200 has a 126 MB L2: the CG vectors of the single-RHS configs fit,
+// the matrix does not.  Every global access of the CG kernels therefore carries an explicit
+// eviction priority: streams that are dead after this access (the CSR arrays, AP's last read,
+// x) are evict_first, vectors that the NEXT kernel re-reads (p for the SpMV gathers, r) are
+// evict_last.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t make_policy_evict_first()
+{
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+
+__device__ __forceinline__ uint64_t make_policy_evict_last()
+{
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+
+__device__ __forceinline__ double2 ld_f64x2_hint(const double *p, uint64_t pol)
+{
+    double2 v;
+    asm volatile("ld.global.L2::cache_hint.v2.f64 {%0, %1}, [%2], %3;" : "=d"(v.x), "=d"(v.y) : "l"(p), "l"(pol));
+    return v;
+}
+
+__device__ __forceinline__ double ld_f64_hint(const double *p, uint64_t pol)
+{
+    double v;
+    asm volatile("ld.global.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(pol));
+    return v;
+}
+
+// read-only (nc) scalar gather with an L2 eviction priority
+__device__ __forceinline__ double ldg_hint(const double *p, uint64_t pol)
+{
+    double v;
+    asm volatile("ld.global.nc.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(pol));
+    return v;
+}
+
+__device__ __forceinline__ float ldg_hint(const float *p, uint64_t pol)
+{
+    float v;
+    asm volatile("ld.global.nc.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(v) : "l"(p), "l"(pol));
+    return v;
+}
+
+__device__ __forceinline__ void st_f64x2_hint(double *p, double2 v, uint64_t pol)
+{
+    asm volatile("st.global.L2::cache_hint.v2.f64 [%0], {%1, %2}, %3;" ::"l"(p), "d"(v.x), "d"(v.y), "l"(pol) : "memory");
+}
+
+__device__ __forceinline__ void st_f64_hint(double *p, double v, uint64_t pol)
+{
+    asm volatile("st.global.L2::cache_hint.f64 [%0], %1, %2;" ::"l"(p), "d"(v), "l"(pol) : "memory");
+}
+
+// ---------------------------------------------------------------------------------------
 // "last CTA done" election (threadFenceReduction pattern): every CTA publishes its global
 // writes, takes a ticket, and the CTA that draws the last ticket runs the serial epilogue
 // (carry fix-up, deterministic reduction of the per-CTA partials, CG scalars).  The ticket

@@ -142,8 +142,17 @@ __global__ void tile_maxlen_kernel(const int *__restrict__ ro, const int2 *__res
     if (lane == 0) out[t] = mx;
 }
 
+// CTAs per SM the shared-memory footprint allows (227 KB usable, 1 KB reserved per CTA)
+template <typename V, int IPT, int STAGES>
+constexpr int spmv_ctas_per_sm()
+{
+    constexpr size_t per_cta = SpmvSmem<V, IPT>::STAGE_BYTES * STAGES + 4096;
+    constexpr int n = (int)((size_t)227 * 1024 / per_cta);
+    return n < 1 ? 1 : (n > 4 ? 4 : n);
+}
+
 template <typename V, int IPT, int STAGES, bool DOT>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, spmv_ctas_per_sm<V, IPT, STAGES>())
 spmv_kernel(SpmvArgs<V> a, CgScalars cg)
 {
     using SM = SpmvSmem<V, IPT>;
@@ -179,6 +188,7 @@ spmv_kernel(SpmvArgs<V> a, CgScalars cg)
 
     // producer: one thread arms the stage's mbarrier and issues the three bulk copies of a tile
     const uint64_t pol_stream = l2_policy_evict_first();
+    const uint64_t pol_keep = l2_policy_evict_last();    // x is gathered ~(nnz/n) times per SpMV
     auto issue = [&](int t, int s) {
         const int2 lo = a.tile_xy[t], hi = a.tile_xy[t + 1];
         const int yc = lo.y & ~3;                                   // 16 B aligned column start
@@ -206,10 +216,17 @@ spmv_kernel(SpmvArgs<V> a, CgScalars cg)
 
     V dot = 0;
 
+    // tile metadata is fetched one tile ahead so its latency hides behind the previous tile
+    int2 nxt_lo = make_int2(0, 0), nxt_hi = make_int2(0, 0);
+    int nxt_ml = 0;
+    if (t0 < t1) { nxt_lo = a.tile_xy[t0]; nxt_hi = a.tile_xy[t0 + 1]; nxt_ml = a.tile_maxlen[t0]; }
+
     for (int t = t0; t < t1; ++t) {
         const int it = t - t0, s = it % STAGES, par = it & 1;
         const uint32_t parity = (uint32_t)(it / STAGES) & 1u;
-        const int2 lo = a.tile_xy[t], hi = a.tile_xy[t + 1];
+        const int2 lo = nxt_lo, hi = nxt_hi;
+        const int tile_ml = nxt_ml;
+        if (t + 1 < t1) { nxt_lo = hi; nxt_hi = a.tile_xy[t + 2]; nxt_ml = a.tile_maxlen[t + 1]; }
         const int x0 = lo.x, y0 = lo.y;
         const int rows = hi.x - x0, nz = hi.y - y0, items = rows + nz;
         const int yc = y0 & ~3, yv = y0 & ~(EPV - 1), rb = (x0 + 1) & ~3;
@@ -220,7 +237,7 @@ spmv_kernel(SpmvArgs<V> a, CgScalars cg)
 
         mbar_wait(&s_full[s], parity);
 
-        if (a.tile_maxlen[t] <= kRowPathMaxLen) {
+        if (tile_ml <= kRowPathMaxLen) {
             // ---- regular tile: fused thread-per-row path -------------------------------------------
             // Thread i owns local row i (and i+256, interleaved for ILP): it reads the row's values
             // and columns from the stage buffers, gathers x (adjacent lanes = adjacent rows, so the
@@ -251,12 +268,12 @@ spmv_kernel(SpmvArgs<V> a, CgScalars cg)
 #pragma unroll
                     for (int j = 0; j < UB; ++j) {
                         va[j] = 0; xa[j] = 0;
-                        if (begA + j < endA) { va[j] = pvv[begA + j]; xa[j] = __ldg(a.x + pc[begA + j]); }
+                        if (begA + j < endA) { va[j] = pvv[begA + j]; xa[j] = ldg_hint(a.x + pc[begA + j], pol_keep); }
                     }
 #pragma unroll
                     for (int j = 0; j < UB; ++j) {
                         vb[j] = 0; xb[j] = 0;
-                        if (begB + j < endB) { vb[j] = pvv[begB + j]; xb[j] = __ldg(a.x + pc[begB + j]); }
+                        if (begB + j < endB) { vb[j] = pvv[begB + j]; xb[j] = ldg_hint(a.x + pc[begB + j], pol_keep); }
                     }
 #pragma unroll
                     for (int j = 0; j < UB; ++j) sumA += va[j] * xa[j];
@@ -306,7 +323,7 @@ spmv_kernel(SpmvArgs<V> a, CgScalars cg)
                             c[0] = cc.x; c[1] = cc.y; c[2] = cc.z; c[3] = cc.w;
                         }
 #pragma unroll
-                        for (int e = 0; e < EPV; ++e) xv[q][e] = __ldg(a.x + c[e]);
+                        for (int e = 0; e < EPV; ++e) xv[q][e] = ldg_hint(a.x + c[e], pol_keep);
                     }
                 }
 #pragma unroll
