@@ -33,6 +33,7 @@ cudaStream_t g_stream = nullptr;       // the stream in use (own or caller's)
 int g_device = -1;
 int g_sms = 0;
 long long g_launches = 0;
+long long *g_timing = nullptr;   // device debug counters (SMLE_TIMING builds)
 
 int fail(int code, const char *fmt, ...)
 {
@@ -230,15 +231,17 @@ int launch_merge_t(smle_csr_t a, const V *X, V *Y, int k, const CgScalars &cg, b
 }
 
 // k == 1: the TMA-staged single-vector kernel (smle_spmv.cuh)
-//   IPT    merge items per thread per tile (tile = 256*IPT items)
-//   STAGES tiles in flight per CTA
-// The default was picked from the sweep in profiles/ (SMLE_SPMV_CFG=<ipt>x<stages> overrides it).
-template <typename V, int IPT, int STAGES, bool DOT>
+//   THREADS threads per CTA
+//   IPT     merge items per thread per tile (tile = THREADS*IPT items)
+//   STAGES  tiles in flight per CTA
+// The default was picked from the sweep in profiles/ (SMLE_SPMV_CFG=<threads>x<ipt>x<stages>
+// overrides it for experiments).
+template <typename V, int THREADS, int IPT, int STAGES, bool DOT>
 int launch_spmv_t(smle_csr_t a, const V *x, V *y, const CgScalars &cg, bool dry)
 {
-    using SM = SpmvSmem<V, IPT>;
+    using SM = SpmvSmem<V, THREADS, IPT>;
     constexpr size_t smem = SM::STAGE_BYTES * STAGES;
-    auto kern = spmv_kernel<V, IPT, STAGES, DOT>;
+    auto kern = spmv_kernel<V, THREADS, IPT, STAGES, DOT>;
     Partition *p;
     int rc = get_partition(a, SM::TILE, &p);
     if (rc) return rc;
@@ -247,7 +250,7 @@ int launch_spmv_t(smle_csr_t a, const V *x, V *y, const CgScalars &cg, bool dry)
     static int occ = 0;   // per instantiation
     if (!occ) {
         CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kThreads, smem));
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, THREADS + 32, smem));
         if (occ < 1) return fail(SMLE_ERR_CUDA, "spmv_kernel does not fit on an SM (%zu B smem)", smem);
         if (occ > 8) occ = 8;
     }
@@ -265,33 +268,37 @@ int launch_spmv_t(smle_csr_t a, const V *x, V *y, const CgScalars &cg, bool dry)
     args.carry_row = a->carry_row; args.carry_val = (V *)a->carry_val;
     args.dot_part = (V *)a->dot_part; args.fix_part = (V *)a->fix_part;
     args.ticket = a->ticket;
-    kern<<<grid, kThreads, smem, g_stream>>>(args, cg);
+    args.timing = g_timing;
+    { static int dbg = -1; if (dbg < 0) { const char *e = getenv("SMLE_SPMV_DEBUG"); dbg = e ? atoi(e) : 0; } args.debug_flags = dbg; }
+    kern<<<grid, THREADS + 32, smem, g_stream>>>(args, cg);   // + the producer warp
     ++g_launches;
     return check_launch("spmv_kernel");
 }
 
-constexpr int kSpmvIPT = 12, kSpmvStages = 2;   // default configuration
+constexpr int kSpmvThreads = 256, kSpmvIPT = 12, kSpmvStages = 2;   // default configuration
 
-int spmv_cfg()
+int spmv_cfg()   // threads*10000 + ipt*100 + stages
 {
     static int cfg = -1;
     if (cfg < 0) {
-        cfg = kSpmvIPT * 10 + kSpmvStages;
+        cfg = kSpmvThreads * 10000 + kSpmvIPT * 100 + kSpmvStages;
         const char *e = getenv("SMLE_SPMV_CFG");
-        int i = 0, st = 0;
-        if (e && sscanf(e, "%dx%d", &i, &st) == 2) cfg = i * 10 + st;
+        int th = 0, i = 0, st = 0;
+        if (e && sscanf(e, "%dx%dx%d", &th, &i, &st) == 3) cfg = th * 10000 + i * 100 + st;
     }
     return cfg;
 }
 
-int spmv_tile_items() { return kThreads * (spmv_cfg() / 10); }
+int spmv_tile_items() { return (spmv_cfg() / 10000) * ((spmv_cfg() / 100) % 100); }
 
 template <typename V, bool DOT>
 int launch_spmv(smle_csr_t a, const V *x, V *y, const CgScalars &cg, bool dry)
 {
     switch (spmv_cfg()) {
-#define SMLE_CFG(i, st) case i * 10 + st: return launch_spmv_t<V, i, st, DOT>(a, x, y, cg, dry);
-        SMLE_CFG(12, 2) SMLE_CFG(8, 2) SMLE_CFG(8, 3) SMLE_CFG(6, 2) SMLE_CFG(6, 3) SMLE_CFG(16, 2) SMLE_CFG(12, 3)
+#define SMLE_CFG(th, i, st) case th * 10000 + i * 100 + st: return launch_spmv_t<V, th, i, st, DOT>(a, x, y, cg, dry);
+        SMLE_CFG(256, 12, 2) SMLE_CFG(128, 12, 2)
+        SMLE_CFG(256, 8, 2) SMLE_CFG(256, 8, 3) SMLE_CFG(256, 6, 4) SMLE_CFG(256, 6, 3) SMLE_CFG(256, 4, 4) SMLE_CFG(256, 4, 6)
+        SMLE_CFG(512, 6, 2) SMLE_CFG(512, 4, 3)
 #undef SMLE_CFG
     }
     return fail(SMLE_ERR_ARG, "unsupported SMLE_SPMV_CFG");
@@ -759,6 +766,18 @@ int smle_cg_multi_f64(smle_csr_t a, const double *B, double *X, int k, int max_i
 int smle_cg_run_fixed_f64(smle_csr_t a, const double *B, double *X, int k, int iters)
 {
     return cg_solve(a, B, X, k, iters, -1.0, 1, nullptr, nullptr, 0, nullptr, nullptr);
+}
+
+// debug: per-phase cycle counters of the SpMV kernel (meaningful only in -DSMLE_TIMING builds)
+int smle_debug_timing(long long *out4, int reset)
+{
+    int rc = ensure_init();
+    if (rc) return rc;
+    if (!g_timing) { CU(cudaMalloc(&g_timing, 64)); CU(cudaMemset(g_timing, 0, 64)); }
+    CU(cudaStreamSynchronize(g_stream));
+    if (out4) CU(cudaMemcpy(out4, g_timing, 64, cudaMemcpyDeviceToHost));
+    if (reset) CU(cudaMemset(g_timing, 0, 64));
+    return SMLE_OK;
 }
 
 int smle_cg_profile_f64(smle_csr_t a, const double *B, double *X, int k, int iters, float *ms_per_kernel)

@@ -186,17 +186,17 @@ __device__ __forceinline__ bool last_cta_election(unsigned int *ticket, unsigned
 // ---------------------------------------------------------------------------------------
 // Deterministic column-wise reduction of per-CTA partials by ONE CTA:
 //   out[c] = sum_e (src1[e*k+c] + (src2 ? src2[e*k+c] : 0)),  e in [0, entries)
-// The order of additions is fixed by (kThreads, entries, k) only, so results are
-// reproducible run to run.  red: shared scratch of kThreads values.
+// The order of additions is fixed by (blockDim.x, entries, k) only, so results are
+// reproducible run to run.  red: shared scratch of blockDim.x values.
 // ---------------------------------------------------------------------------------------
 template <typename V>
 __device__ __forceinline__ void cta_reduce_columns(const V *src1, const V *src2, int entries, int k,
                                                    V *out, V *red)
 {
-    const int tid = threadIdx.x;
-    for (int cbase = 0; cbase < k; cbase += kThreads) {
-        const int kk = min(k - cbase, kThreads);       // columns in this pass
-        const int parts = kThreads / kk;               // threads cooperating per column
+    const int tid = threadIdx.x, nthreads = blockDim.x;
+    for (int cbase = 0; cbase < k; cbase += nthreads) {
+        const int kk = min(k - cbase, nthreads);       // columns in this pass
+        const int parts = nthreads / kk;               // threads cooperating per column
         const int c = tid % kk, part = tid / kk;
         V s = 0;
         if (part < parts) {

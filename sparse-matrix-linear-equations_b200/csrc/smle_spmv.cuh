@@ -104,11 +104,13 @@ struct SpmvArgs {
     V *dot_part;                       // [gridDim.x]  (DOT)
     V *fix_part;                       // [gridDim.x]  (DOT)
     unsigned int *ticket;
+    long long *timing;                 // debug counters (only read with -DSMLE_TIMING)
+    int debug_flags;                   // 1: skip compute (stream-only ceiling), 2: skip gathers
 };
 
-template <typename V, int IPT>
+template <typename V, int THREADS, int IPT>
 struct SpmvSmem {
-    static constexpr int TILE = kThreads * IPT;
+    static constexpr int TILE = THREADS * IPT;
     static constexpr int EPV = 16 / (int)sizeof(V);                  // values per 16 bytes
     static constexpr int COL_WORDS = TILE + 8;                       // staged column indices
     static constexpr int VAL_ELEMS = TILE + 2 * EPV;                 // staged values
@@ -142,28 +144,54 @@ __global__ void tile_maxlen_kernel(const int *__restrict__ ro, const int2 *__res
     if (lane == 0) out[t] = mx;
 }
 
-// CTAs per SM the shared-memory footprint allows (227 KB usable, 1 KB reserved per CTA)
-template <typename V, int IPT, int STAGES>
-constexpr int spmv_ctas_per_sm()
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
 {
-    constexpr size_t per_cta = SpmvSmem<V, IPT>::STAGE_BYTES * STAGES + 4096;
-    constexpr int n = (int)((size_t)227 * 1024 / per_cta);
-    return n < 1 ? 1 : (n > 4 ? 4 : n);
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
-template <typename V, int IPT, int STAGES, bool DOT>
-__global__ void __launch_bounds__(kThreads, spmv_ctas_per_sm<V, IPT, STAGES>())
+// barrier among the THREADS consumer threads only (the producer warp never joins it)
+template <int THREADS>
+__device__ __forceinline__ void consumer_sync()
+{
+    asm volatile("bar.sync 1, %0;" ::"n"(THREADS) : "memory");
+}
+
+// CTAs per SM the shared-memory footprint allows (227 KB usable, ~1 KB reserved per CTA)
+template <typename V, int THREADS, int IPT, int STAGES>
+constexpr int spmv_ctas_per_sm()
+{
+    constexpr size_t per_cta = SpmvSmem<V, THREADS, IPT>::STAGE_BYTES * STAGES + 4096;
+    constexpr int by_smem = (int)((size_t)227 * 1024 / per_cta);
+    constexpr int by_threads = 2048 / (THREADS + 32);
+    constexpr int n = by_smem < by_threads ? by_smem : by_threads;
+    return n < 1 ? 1 : (n > 8 ? 8 : n);
+}
+
+// ---------------------------------------------------------------------------------------
+// spmv_kernel: THREADS consumer threads + one producer warp per CTA.
+//
+//   producer warp (one elected lane): for every tile of the CTA, waits until the stage buffer
+//       is released (mbarrier "empty", one arrival per consumer warp) and issues the three
+//       bulk copies of the tile (column indices, values, row offsets) onto the stage's "full"
+//       mbarrier.  It runs STAGES tiles ahead and never touches the data.
+//   consumers: wait "full" -> phase A (value * x[column] in place, all gathers of a thread in
+//       flight together) -> consumer barrier -> phase B (row sums) -> arrive on "empty".
+//       There is ONE consumer barrier per regular tile and no CTA-wide barrier at all.
+// ---------------------------------------------------------------------------------------
+template <typename V, int THREADS, int IPT, int STAGES, bool DOT>
+__global__ void __launch_bounds__(THREADS + 32, spmv_ctas_per_sm<V, THREADS, IPT, STAGES>())
 spmv_kernel(SpmvArgs<V> a, CgScalars cg)
 {
-    using SM = SpmvSmem<V, IPT>;
+    using SM = SpmvSmem<V, THREADS, IPT>;
+    constexpr int NW = THREADS / 32;
     constexpr int EPV = SM::EPV;
 
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    __shared__ uint64_t s_full[STAGES];
-    __shared__ int s_wkey_first[kWarps], s_wkey_last[kWarps];
-    __shared__ V s_wsum[kWarps];
+    __shared__ uint64_t s_full[STAGES], s_empty[STAGES];
+    __shared__ int s_wkey_first[NW], s_wkey_last[NW];
+    __shared__ V s_wsum[NW];
     __shared__ V s_carry[2];                 // tile carry, double-buffered by tile parity
-    __shared__ V s_red[kThreads];
+    __shared__ V s_red[THREADS + 32];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
@@ -186,140 +214,88 @@ spmv_kernel(SpmvArgs<V> a, CgScalars cg)
                                        (size_t)SM::VAL_ELEMS * sizeof(V));
     };
 
-    // producer: one thread arms the stage's mbarrier and issues the three bulk copies of a tile
-    const uint64_t pol_stream = l2_policy_evict_first();
-    const uint64_t pol_keep = l2_policy_evict_last();    // x is gathered ~(nnz/n) times per SpMV
-    auto issue = [&](int t, int s) {
-        const int2 lo = a.tile_xy[t], hi = a.tile_xy[t + 1];
-        const int yc = lo.y & ~3;                                   // 16 B aligned column start
-        const int yv = lo.y & ~(EPV - 1);                           // 16 B aligned value start
-        const int rb = (lo.x + 1) & ~3;                             // 16 B aligned row-offset start
-        const uint32_t nb_col = (uint32_t)((hi.y - yc + 3) & ~3) * 4u;
-        const uint32_t nb_val = (uint32_t)((hi.y - yv + EPV - 1) & ~(EPV - 1)) * (uint32_t)sizeof(V);
-        const uint32_t nb_ro = (uint32_t)((hi.x + 2 - rb + 3) & ~3) * 4u;
-        const uint32_t total = nb_col + nb_val + nb_ro;             // nb_ro > 0 always
-        mbar_expect_tx(&s_full[s], total);
-        if (nb_col) tma_load_1d(stage_col(s), a.ci + yc, nb_col, &s_full[s], pol_stream);
-        if (nb_val) tma_load_1d(stage_val(s), a.va + yv, nb_val, &s_full[s], pol_stream);
-        tma_load_1d(stage_ro(s), a.ro + rb, nb_ro, &s_full[s], pol_stream);
-    };
-
     if (tid == 0) {
-        for (int s = 0; s < STAGES; ++s) mbar_init(&s_full[s], 1);
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&s_full[s], 1); mbar_init(&s_empty[s], NW); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         s_carry[0] = 0; s_carry[1] = 0;
     }
     __syncthreads();
-    if (tid == 0) {
-        for (int s = 0; s < STAGES && t0 + s < t1; ++s) issue(t0 + s, s);
-    }
 
     V dot = 0;
 
-    // tile metadata is fetched one tile ahead so its latency hides behind the previous tile
-    int2 nxt_lo = make_int2(0, 0), nxt_hi = make_int2(0, 0);
-    int nxt_ml = 0;
-    if (t0 < t1) { nxt_lo = a.tile_xy[t0]; nxt_hi = a.tile_xy[t0 + 1]; nxt_ml = a.tile_maxlen[t0]; }
-
-    for (int t = t0; t < t1; ++t) {
-        const int it = t - t0, s = it % STAGES, par = it & 1;
-        const uint32_t parity = (uint32_t)(it / STAGES) & 1u;
-        const int2 lo = nxt_lo, hi = nxt_hi;
-        const int tile_ml = nxt_ml;
-        if (t + 1 < t1) { nxt_lo = hi; nxt_hi = a.tile_xy[t + 2]; nxt_ml = a.tile_maxlen[t + 1]; }
-        const int x0 = lo.x, y0 = lo.y;
-        const int rows = hi.x - x0, nz = hi.y - y0, items = rows + nz;
-        const int yc = y0 & ~3, yv = y0 & ~(EPV - 1), rb = (x0 + 1) & ~3;
-        int *s_col = stage_col(s);
-        V *s_val = stage_val(s);
-        const int *s_re = stage_ro(s) + (x0 + 1 - rb);   // s_re[i] = end offset of local row i
-        const int voff = y0 - yv;                          // s_val index of the tile's first nonzero
-
-        mbar_wait(&s_full[s], parity);
-
-        if (tile_ml <= kRowPathMaxLen) {
-            // ---- regular tile: fused thread-per-row path -------------------------------------------
-            // Thread i owns local row i (and i+256, interleaved for ILP): it reads the row's values
-            // and columns from the stage buffers, gathers x (adjacent lanes = adjacent rows, so the
-            // gathers coalesce for banded matrices), and writes y[row] directly -- coalesced, no
-            // product staging, no scan.  Pseudo-row `rows` is the trailing part of row hi.x: its sum
-            // is the tile carry-out; row 0 starts from the carry-in.
-            const int *pc = s_col + (y0 - yc);
-            const V *pvv = s_val + voff;
-            for (int i = tid; i <= rows; i += 2 * kThreads) {
-                const int iB = i + kThreads;
-                const bool hasB = iB <= rows;
-                int begA = (i == 0) ? 0 : s_re[i - 1] - y0;
-                const int endA = (i == rows) ? nz : s_re[i] - y0;
-                int begB = 0, endB = 0;
-                if (hasB) {
-                    begB = s_re[iB - 1] - y0;
-                    endB = (iB == rows) ? nz : s_re[iB] - y0;
+    if (warp == NW) {
+        // =============================== producer warp ===========================================
+        if (lane == 0) {
+            const uint64_t pol_stream = l2_policy_evict_first();   // the matrix is read once per SpMV
+            int2 lo = (t0 < t1) ? a.tile_xy[t0] : make_int2(0, 0);
+            for (int t = t0; t < t1; ++t) {
+                const int it = t - t0, s = it % STAGES;
+                const int2 hi = a.tile_xy[t + 1];
+                if (it >= STAGES) {
+                    mbar_wait(&s_empty[s], (uint32_t)(it / STAGES - 1) & 1u);
+                    fence_proxy_async();
                 }
-                V xrA = 0, xrB = 0;
-                if constexpr (DOT) {
-                    if (i < rows) xrA = __ldg(a.x + x0 + i);
-                    if (hasB && iB < rows) xrB = __ldg(a.x + x0 + iB);
-                }
-                V sumA = (i == 0) ? s_carry[par] : V(0), sumB = 0;
-                while (begA < endA || begB < endB) {
-                    constexpr int UB = 8;
-                    V va[UB], xa[UB], vb[UB], xb[UB];
-#pragma unroll
-                    for (int j = 0; j < UB; ++j) {
-                        va[j] = 0; xa[j] = 0;
-                        if (begA + j < endA) { va[j] = pvv[begA + j]; xa[j] = ldg_hint(a.x + pc[begA + j], pol_keep); }
-                    }
-#pragma unroll
-                    for (int j = 0; j < UB; ++j) {
-                        vb[j] = 0; xb[j] = 0;
-                        if (begB + j < endB) { vb[j] = pvv[begB + j]; xb[j] = ldg_hint(a.x + pc[begB + j], pol_keep); }
-                    }
-#pragma unroll
-                    for (int j = 0; j < UB; ++j) sumA += va[j] * xa[j];
-#pragma unroll
-                    for (int j = 0; j < UB; ++j) sumB += vb[j] * xb[j];
-                    begA += UB; begB += UB;
-                }
-                if (i < rows) {
-                    a.y[x0 + i] = sumA;
-                    if constexpr (DOT) dot += sumA * xrA;
-                } else {
-                    s_carry[par ^ 1] = sumA;
-                }
-                if (hasB) {
-                    if (iB < rows) {
-                        a.y[x0 + iB] = sumB;
-                        if constexpr (DOT) dot += sumB * xrB;
-                    } else {
-                        s_carry[par ^ 1] = sumB;
-                    }
-                }
+                const int yc = lo.y & ~3;                                   // 16 B aligned column start
+                const int yv = lo.y & ~(EPV - 1);                           // 16 B aligned value start
+                const int rb = (lo.x + 1) & ~3;                             // 16 B aligned row-offset start
+                const uint32_t nb_col = (uint32_t)((hi.y - yc + 3) & ~3) * 4u;
+                const uint32_t nb_val = (uint32_t)((hi.y - yv + EPV - 1) & ~(EPV - 1)) * (uint32_t)sizeof(V);
+                const uint32_t nb_ro = (uint32_t)((hi.x + 2 - rb + 3) & ~3) * 4u;
+                mbar_expect_tx(&s_full[s], nb_col + nb_val + nb_ro);        // nb_ro > 0 always
+                if (nb_col) tma_load_1d(stage_col(s), a.ci + yc, nb_col, &s_full[s], pol_stream);
+                if (nb_val) tma_load_1d(stage_val(s), a.va + yv, nb_val, &s_full[s], pol_stream);
+                tma_load_1d(stage_ro(s), a.ro + rb, nb_ro, &s_full[s], pol_stream);
+                lo = hi;
             }
-        } else {
-            // ---- general tile, phase A: products in place -------------------------------------------
-            // all shared loads and all gathers of a thread are issued before the first product is
-            // written back, so MAXIT*EPV independent global loads are in flight per thread.  The
-            // 16-byte groups at the edges may include nonzeros of the neighbouring tiles: their
-            // products are computed (the column is valid; the slack behind ci is zero-filled) and
-            // never read.
+        }
+    } else {
+        // =============================== consumer warps ==========================================
+        const uint64_t pol_keep = l2_policy_evict_last();    // x is gathered ~(nnz/n) times per SpMV
+
+        // tile metadata is fetched one tile ahead so its latency hides behind the previous tile
+        int2 nxt_lo = make_int2(0, 0), nxt_hi = make_int2(0, 0);
+        int nxt_ml = 0;
+        if (t0 < t1) { nxt_lo = a.tile_xy[t0]; nxt_hi = a.tile_xy[t0 + 1]; nxt_ml = a.tile_maxlen[t0]; }
+
+        for (int t = t0; t < t1; ++t) {
+            const int it = t - t0, s = it % STAGES, par = it & 1;
+            const uint32_t parity = (uint32_t)(it / STAGES) & 1u;
+            const int2 lo = nxt_lo, hi = nxt_hi;
+            const int tile_ml = nxt_ml;
+            if (t + 1 < t1) { nxt_lo = hi; nxt_hi = a.tile_xy[t + 2]; nxt_ml = a.tile_maxlen[t + 1]; }
+            const int x0 = lo.x, y0 = lo.y;
+            const int rows = hi.x - x0, nz = hi.y - y0, items = rows + nz;
+            const int yc = y0 & ~3, yv = y0 & ~(EPV - 1), rb = (x0 + 1) & ~3;
+            int *s_col = stage_col(s);
+            V *s_val = stage_val(s);
+            const int *s_re = stage_ro(s) + (x0 + 1 - rb);   // s_re[i] = end offset of local row i
+            const V *s_prod = s_val + (y0 - yv);               // s_prod[z] = product of local nonzero z
+
+            mbar_wait(&s_full[s], parity);
+
+            if (!(a.debug_flags & 1)) {
+            // ---- phase A: products in place ----------------------------------------------------
+            // Coalesced and branch-free: 16-byte groups of values and their columns are read with
+            // 128/64-bit shared loads, ALL gathers of the thread are issued before the first product
+            // is formed (MAXIT*EPV independent global loads in flight per thread), and the products
+            // replace the values.  Groups at the tile edges may include nonzeros of the neighbouring
+            // tiles: their products are computed (the column is valid; the slack behind ci is
+            // zero-filled) and never read.
             {
                 const int nvec = (hi.y - yv + EPV - 1) / EPV;   // 16-byte groups staged
-                constexpr int MAXIT = (SM::VAL_ELEMS / EPV + kThreads - 1) / kThreads;
-                V v[MAXIT][EPV];
+                constexpr int MAXIT = (SM::VAL_ELEMS / EPV + THREADS - 1) / THREADS;
                 V xv[MAXIT][EPV];
-                const int cshift = yv - yc;                     // s_col index of value group 0
+                const int *cbase = s_col + (yv - yc);
 #pragma unroll
                 for (int q = 0; q < MAXIT; ++q) {
-                    const int g = tid + q * kThreads;           // group index
+                    const int g = tid + q * THREADS;           // group index
                     if (g < nvec) {
                         int c[EPV];
-                        ld_vec<V, EPV>(v[q], s_val + g * EPV);
                         if constexpr (EPV == 2) {
-                            int2 cc = *reinterpret_cast<const int2 *>(s_col + cshift + g * EPV);
+                            int2 cc = *reinterpret_cast<const int2 *>(cbase + g * EPV);
                             c[0] = cc.x; c[1] = cc.y;
                         } else {
-                            int4 cc = *reinterpret_cast<const int4 *>(s_col + cshift + g * EPV);
+                            int4 cc = *reinterpret_cast<const int4 *>(cbase + g * EPV);
                             c[0] = cc.x; c[1] = cc.y; c[2] = cc.z; c[3] = cc.w;
                         }
 #pragma unroll
@@ -328,105 +304,161 @@ spmv_kernel(SpmvArgs<V> a, CgScalars cg)
                 }
 #pragma unroll
                 for (int q = 0; q < MAXIT; ++q) {
-                    const int g = tid + q * kThreads;
+                    const int g = tid + q * THREADS;
                     if (g < nvec) {
+                        V v[EPV];
+                        ld_vec<V, EPV>(v, s_val + g * EPV);
 #pragma unroll
-                        for (int e = 0; e < EPV; ++e) v[q][e] *= xv[q][e];
-                        st_vec<V, EPV>(s_val + g * EPV, v[q]);
+                        for (int e = 0; e < EPV; ++e) v[e] *= xv[q][e];
+                        st_vec<V, EPV>(s_val + g * EPV, v);
                     }
                 }
             }
-            __syncthreads();
+            consumer_sync<THREADS>();
 
-            // ---- general tile, phase B: merge-path walk, IPT items per thread ------------------------
-            V *s_y = reinterpret_cast<V *>(s_col);        // row buffer (columns are consumed)
-            const bool y_in_smem = rows <= SM::YBUF_ROWS;
-            const int d0 = min(tid * IPT, items);
-            int r_start;
-            {
-                // MergePathSearch (merge_based.hpp:22-44) on the staged row-end offsets
-                int l = max(d0 - nz, 0), h = min(d0, rows);
-                while (l < h) {
-                    const int mid = (l + h) >> 1;
-                    if (s_re[mid] - y0 <= d0 - mid - 1) l = mid + 1; else h = mid;
-                }
-                r_start = l;
-            }
-            int r = r_start;
-            int z = d0 - r;
-            V acc = (tid == 0) ? s_carry[par] : V(0);
-            int cur_end = s_re[r] - y0;
-            const int n_items = min(IPT, items - d0);
+            if (tile_ml <= kRowPathMaxLen) {
+                // ---- phase B, regular tile: one thread per row (two rows interleaved) ----------------
+                // Adjacent lanes own adjacent rows, y is written coalesced, there is no scan.
+                // Pseudo-row `rows` is the trailing part of row hi.x: its sum is the tile carry-out;
+                // row 0 starts from the carry-in.
+                for (int i = tid; i <= rows; i += 2 * THREADS) {
+                    const int iB = i + THREADS;
+                    const bool hasB = iB <= rows;
+                    int begA = (i == 0) ? 0 : s_re[i - 1] - y0;
+                    const int endA = (i == rows) ? nz : s_re[i] - y0;
+                    int begB = 0, endB = 0;
+                    if (hasB) {
+                        begB = s_re[iB - 1] - y0;
+                        endB = (iB == rows) ? nz : s_re[iB] - y0;
+                    }
+                    V xrA = 0, xrB = 0;
+                    if constexpr (DOT) {
+                        if (i < rows) xrA = __ldg(a.x + x0 + i);
+                        if (hasB && iB < rows) xrB = __ldg(a.x + x0 + iB);
+                    }
+                    V sumA = (i == 0) ? s_carry[par] : V(0), sumB = 0;
+                    do {
+                        constexpr int UB = 8;
+                        V pa[UB], pb[UB];
 #pragma unroll
-            for (int i = 0; i < IPT; ++i) {
-                const bool live = i < n_items;
-                const bool is_nz = live && (z < cur_end);
-                const V pv = s_val[voff + z];             // always inside the stage buffer
-                if (is_nz) { acc += pv; ++z; }
-                if (live && !is_nz) {
-                    if (y_in_smem) s_y[r] = acc; else a.y[x0 + r] = acc;
-                    acc = 0;
-                    ++r;
-                    cur_end = s_re[r] - y0;
-                }
-            }
-
-            // carries: inclusive segmented scan keyed by the row in progress
-            const int key = x0 + r;
-            V sc = acc;
-            {
-                const int pkey = __shfl_up_sync(0xffffffffu, key, 1);
-                const bool same = lane > 0 && pkey == key;
-                if (__any_sync(0xffffffffu, same)) {   // a row spans several threads of this warp
+                        for (int j = 0; j < UB; ++j) pa[j] = (begA + j < endA) ? s_prod[begA + j] : V(0);
 #pragma unroll
-                    for (int d = 1; d < 32; d <<= 1) {
-                        const int okey = __shfl_up_sync(0xffffffffu, key, d);
-                        const V o = __shfl_up_sync(0xffffffffu, sc, d);
-                        if (lane >= d && okey == key) sc += o;
+                        for (int j = 0; j < UB; ++j) pb[j] = (begB + j < endB) ? s_prod[begB + j] : V(0);
+#pragma unroll
+                        for (int j = 0; j < UB; ++j) sumA += pa[j];
+#pragma unroll
+                        for (int j = 0; j < UB; ++j) sumB += pb[j];
+                        begA += UB; begB += UB;
+                    } while (begA < endA || begB < endB);
+                    if (i < rows) {
+                        a.y[x0 + i] = sumA;
+                        if constexpr (DOT) dot += sumA * xrA;
+                    } else {
+                        s_carry[par ^ 1] = sumA;
+                    }
+                    if (hasB) {
+                        if (iB < rows) {
+                            a.y[x0 + iB] = sumB;
+                            if constexpr (DOT) dot += sumB * xrB;
+                        } else {
+                            s_carry[par ^ 1] = sumB;
+                        }
                     }
                 }
-            }
-            if (lane == 31) { s_wkey_last[warp] = key; s_wsum[warp] = sc; }
-            if (lane == 0) s_wkey_first[warp] = key;
-            __syncthreads();
-            // full inclusive value of the previous warps' last threads (rows may chain across warps)
-            V wprev = 0;
-            for (int wi = 0; wi < warp; ++wi) {
-                const bool chain = wi > 0 && s_wkey_first[wi] == s_wkey_last[wi] &&
-                                   s_wkey_last[wi - 1] == s_wkey_last[wi];
-                wprev = s_wsum[wi] + (chain ? wprev : V(0));
-            }
-            const int wprev_key = warp > 0 ? s_wkey_last[warp - 1] : -1;
-            const int wfirst_key = s_wkey_first[warp];
-            const V sfull = sc + ((wfirst_key == key && wprev_key == key) ? wprev : V(0));
-            V carry_in = __shfl_up_sync(0xffffffffu, sfull, 1);
-            if (lane == 0) carry_in = wprev;
-            if (tid == 0) carry_in = 0;   // the tile carry already seeded thread 0's accumulator
-            if (r > r_start) {            // this thread completed row r_start: it owns that entry
-                if (y_in_smem) s_y[r_start] += carry_in;
-                else a.y[x0 + r_start] += carry_in;
-            }
-            if (tid == kThreads - 1) s_carry[par ^ 1] = sfull;   // tile carry-out (row hi.x)
-            __syncthreads();
-
-            // phase C: coalesced row output (+ dot)
-            if (y_in_smem) {
-                for (int i = tid; i < rows; i += kThreads) {
-                    const V v = s_y[i];
-                    a.y[x0 + i] = v;
-                    if constexpr (DOT) dot += v * __ldg(a.x + x0 + i);
+            } else {
+                // ---- phase B, general tile: merge-path walk, IPT items per thread -----------------------
+                V *s_y = reinterpret_cast<V *>(s_col);        // row buffer (columns are consumed)
+                const bool y_in_smem = rows <= SM::YBUF_ROWS;
+                const int d0 = min(tid * IPT, items);
+                int r_start;
+                {
+                    // MergePathSearch (merge_based.hpp:22-44) on the staged row-end offsets
+                    int l = max(d0 - nz, 0), h = min(d0, rows);
+                    while (l < h) {
+                        const int mid = (l + h) >> 1;
+                        if (s_re[mid] - y0 <= d0 - mid - 1) l = mid + 1; else h = mid;
+                    }
+                    r_start = l;
                 }
-            } else if constexpr (DOT) {
-                for (int i = tid; i < rows; i += kThreads) dot += a.y[x0 + i] * __ldg(a.x + x0 + i);
-            }
-        }
-        __syncthreads();   // stage s fully consumed, s_carry[par^1] published
+                int r = r_start;
+                int z = d0 - r;
+                V acc = (tid == 0) ? s_carry[par] : V(0);
+                int cur_end = s_re[r] - y0;
+                const int n_items = min(IPT, items - d0);
+#pragma unroll
+                for (int i = 0; i < IPT; ++i) {
+                    const bool live = i < n_items;
+                    const bool is_nz = live && (z < cur_end);
+                    const V pv = s_prod[z];                   // always inside the stage buffer
+                    if (is_nz) { acc += pv; ++z; }
+                    if (live && !is_nz) {
+                        if (y_in_smem) s_y[r] = acc; else a.y[x0 + r] = acc;
+                        acc = 0;
+                        ++r;
+                        cur_end = s_re[r] - y0;
+                    }
+                }
 
-        if (tid == 0 && t + STAGES < t1) {
+                // carries: inclusive segmented scan keyed by the row in progress
+                const int key = x0 + r;
+                V sc = acc;
+                {
+                    const int pkey = __shfl_up_sync(0xffffffffu, key, 1);
+                    const bool same = lane > 0 && pkey == key;
+                    if (__any_sync(0xffffffffu, same)) {   // a row spans several threads of this warp
+#pragma unroll
+                        for (int d = 1; d < 32; d <<= 1) {
+                            const int okey = __shfl_up_sync(0xffffffffu, key, d);
+                            const V o = __shfl_up_sync(0xffffffffu, sc, d);
+                            if (lane >= d && okey == key) sc += o;
+                        }
+                    }
+                }
+                if (lane == 31) { s_wkey_last[warp] = key; s_wsum[warp] = sc; }
+                if (lane == 0) s_wkey_first[warp] = key;
+                consumer_sync<THREADS>();
+                // full inclusive value of the previous warps' last threads (rows may chain across warps)
+                V wprev = 0;
+                for (int wi = 0; wi < warp; ++wi) {
+                    const bool chain = wi > 0 && s_wkey_first[wi] == s_wkey_last[wi] &&
+                                       s_wkey_last[wi - 1] == s_wkey_last[wi];
+                    wprev = s_wsum[wi] + (chain ? wprev : V(0));
+                }
+                const int wprev_key = warp > 0 ? s_wkey_last[warp - 1] : -1;
+                const int wfirst_key = s_wkey_first[warp];
+                const V sfull = sc + ((wfirst_key == key && wprev_key == key) ? wprev : V(0));
+                V carry_in = __shfl_up_sync(0xffffffffu, sfull, 1);
+                if (lane == 0) carry_in = wprev;
+                if (tid == 0) carry_in = 0;   // the tile carry already seeded thread 0's accumulator
+                if (r > r_start) {            // this thread completed row r_start: it owns that entry
+                    if (y_in_smem) s_y[r_start] += carry_in;
+                    else a.y[x0 + r_start] += carry_in;
+                }
+                if (tid == THREADS - 1) s_carry[par ^ 1] = sfull;   // tile carry-out (row hi.x)
+                consumer_sync<THREADS>();
+
+                // phase C: coalesced row output (+ dot)
+                if (y_in_smem) {
+                    for (int i = tid; i < rows; i += THREADS) {
+                        const V v = s_y[i];
+                        a.y[x0 + i] = v;
+                        if constexpr (DOT) dot += v * __ldg(a.x + x0 + i);
+                    }
+                } else if constexpr (DOT) {
+                    for (int i = tid; i < rows; i += THREADS) dot += a.y[x0 + i] * __ldg(a.x + x0 + i);
+                }
+            }
+            }  // !(debug_flags & 1)
+
+            // release the stage: generic-proxy writes (products, row buffer) ordered before the next
+            // bulk copy, one arrival per consumer warp
             fence_proxy_async();
-            issue(t + STAGES, s);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&s_empty[s]);
         }
     }
+
+    __syncthreads();   // all tiles done (producer warp included); s_carry final
 
     // ---- CTA carry-out ---------------------------------------------------------------------------
     if (tid == 0) {
@@ -438,11 +470,11 @@ spmv_kernel(SpmvArgs<V> a, CgScalars cg)
     if constexpr (DOT) {
 #pragma unroll
         for (int d = 16; d > 0; d >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, d);
-        if (lane == 0) s_wsum[warp] = dot;
+        if (lane == 0 && warp < NW) s_wsum[warp] = dot;
         __syncthreads();
         if (tid == 0) {
             V sdot = 0;
-            for (int wi = 0; wi < kWarps; ++wi) sdot += s_wsum[wi];
+            for (int wi = 0; wi < NW; ++wi) sdot += s_wsum[wi];
             a.dot_part[blockIdx.x] = sdot;
         }
     }
@@ -451,7 +483,7 @@ spmv_kernel(SpmvArgs<V> a, CgScalars cg)
     if (!last_cta_election(a.ticket, gridDim.x)) return;
 
     const int entries = gridDim.x;
-    for (int e = tid; e < entries; e += kThreads) {
+    for (int e = tid; e < entries; e += blockDim.x) {
         const int row = __ldcg(a.carry_row + e);
         V fixdot = 0;
         if (row < a.m && (e == 0 || __ldcg(a.carry_row + e - 1) != row)) {

@@ -23,6 +23,7 @@ with torch.cuda.stream(st):
     ms = e0.elapsed_time(e1) / 50
     b = torch.rand(n, dtype=torch.float64, device="cuda"); xs = torch.empty_like(b)
     k = a.cg_profile(b, xs, 30)
+    a.cg_run_fixed(b.view(n, 1), xs.view(n, 1), 32); torch.cuda.synchronize()
     e0.record(st); a.cg_run_fixed(b.view(n, 1), xs.view(n, 1), 320); e1.record(st); torch.cuda.synchronize()
     it_ms = e0.elapsed_time(e1) / 320
 bytes_ = nnz * 12 + (n + 1) * 4 + 2 * n * 8
@@ -30,7 +31,7 @@ print(f"cfg={os.environ.get('SMLE_SPMV_CFG','default'):6s} spmv {ms*1e3:7.1f} us
 '''
 
 w = sys.argv[1] if len(sys.argv) > 1 else "150"
-for cfg in sys.argv[2:] or ["12x2"]:
+for cfg in sys.argv[2:] or ["256x12x2"]:
     env = dict(os.environ, SMLE_SPMV_CFG=cfg)
     r = subprocess.run([sys.executable, "-c", CHILD, w], env=env, capture_output=True, text=True)
     print(r.stdout.strip() or r.stderr.strip()[-400:], flush=True)
