@@ -297,8 +297,7 @@ int launch_spmv(smle_csr_t a, const V *x, V *y, const CgScalars &cg, bool dry)
     switch (spmv_cfg()) {
 #define SMLE_CFG(th, i, st) case th * 10000 + i * 100 + st: return launch_spmv_t<V, th, i, st, DOT>(a, x, y, cg, dry);
         SMLE_CFG(256, 12, 2) SMLE_CFG(128, 12, 2)
-        SMLE_CFG(256, 8, 2) SMLE_CFG(256, 8, 3) SMLE_CFG(256, 6, 4) SMLE_CFG(256, 6, 3) SMLE_CFG(256, 4, 4) SMLE_CFG(256, 4, 6)
-        SMLE_CFG(512, 6, 2) SMLE_CFG(512, 4, 3)
+        SMLE_CFG(256, 8, 2) SMLE_CFG(256, 8, 3) SMLE_CFG(224, 12, 2) SMLE_CFG(224, 14, 2) SMLE_CFG(480, 6, 2) SMLE_CFG(480, 7, 2)
 #undef SMLE_CFG
     }
     return fail(SMLE_ERR_ARG, "unsupported SMLE_SPMV_CFG");
@@ -449,8 +448,10 @@ int launch_vec(int which, const CgVecArgs &va, const CgScalars &cg, int max_iter
 {
     if (va.k == 1 && which != 0 && getenv("SMLE_VEC_GENERIC") == nullptr) {
         // single right-hand side: 128-bit, unrolled kernels with L2 eviction priorities
+        static int ctas_per_sm = -1;
+        if (ctas_per_sm < 0) { const char *e = getenv("SMLE_VEC_CTAS"); ctas_per_sm = e ? atoi(e) : 2; }
         long long want = ((long long)(va.n >> 1) + kThreads * kVecUnroll - 1) / (kThreads * kVecUnroll);
-        int grid = (int)(want < (long long)g_sms * 8 ? want : (long long)g_sms * 8);
+        int grid = (int)(want < (long long)g_sms * ctas_per_sm ? want : (long long)g_sms * ctas_per_sm);
         if (grid < 1) grid = 1;
         if (which == 1) cg1_update_r_kernel<<<grid, kThreads, 0, g_stream>>>(va, cg);
         else cg1_update_xp_kernel<<<grid, kThreads, 0, g_stream>>>(va, cg);

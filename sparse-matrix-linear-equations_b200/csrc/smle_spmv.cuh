@@ -168,16 +168,50 @@ constexpr int spmv_ctas_per_sm()
 }
 
 // ---------------------------------------------------------------------------------------
+// Row path building blocks (regular tiles).  Thread i owns local row i: adjacent lanes own
+// adjacent rows, so for banded matrices the x gathers of a warp fall into 2-3 cache lines
+// (vs ~8 when lanes walk consecutive nonzeros) and y is written coalesced.  All gathers of a
+// thread are issued before the first FMA; the value is read from shared memory only when the
+// FMA needs it, which keeps the live registers at 2 per gather.
+// ---------------------------------------------------------------------------------------
+template <typename V>
+__device__ __forceinline__ V row_sum(const V *__restrict__ x, const int *pc, const V *pv, int beg, int end)
+{
+    constexpr int UB = 8;
+    V sum = 0;
+    do {
+        V xa[UB];
+#pragma unroll
+        for (int j = 0; j < UB; ++j)
+            if (beg + j < end) xa[j] = __ldg(x + pc[beg + j]);
+#pragma unroll
+        for (int j = 0; j < UB; ++j)
+            if (beg + j < end) sum += pv[beg + j] * xa[j];
+        beg += UB;
+    } while (beg < end);
+    return sum;
+}
+
+// ---------------------------------------------------------------------------------------
 // spmv_kernel: THREADS consumer threads + one producer warp per CTA.
 //
 //   producer warp (one elected lane): for every tile of the CTA, waits until the stage buffer
 //       is released (mbarrier "empty", one arrival per consumer warp) and issues the three
 //       bulk copies of the tile (column indices, values, row offsets) onto the stage's "full"
 //       mbarrier.  It runs STAGES tiles ahead and never touches the data.
-//   consumers: wait "full" -> phase A (value * x[column] in place, all gathers of a thread in
-//       flight together) -> consumer barrier -> phase B (row sums) -> arrive on "empty".
-//       There is ONE consumer barrier per regular tile and no CTA-wide barrier at all.
+//   consumers, regular tile (longest in-tile row segment <= kRowPathMaxLen, the common case):
+//       wait "full" -> thread-per-row gather + FMA straight from the stage buffers -> arrive
+//       on "empty".  NO CTA-wide barrier: warps drift freely across tiles.
+//   consumers, general tile (long or wildly uneven rows): phase A products in place ->
+//       consumer barrier -> merge-path walk of IPT items per thread -> warp-shuffle segmented
+//       scan of the carries -> coalesced row output.
+//   carries: every tile records (first row, has-complete-row, carry-out) in shared memory;
+//       thread 0 chains them in tile order every kChainTiles tiles and the fix-ups are applied
+//       in parallel (reference semantics: merge_based.hpp:137-149, carry added after the row's
+//       owner wrote its partial sum).
 // ---------------------------------------------------------------------------------------
+constexpr int kChainTiles = 512;   // tiles between two carry-chain resolutions of a CTA
+
 template <typename V, int THREADS, int IPT, int STAGES, bool DOT>
 __global__ void __launch_bounds__(THREADS + 32, spmv_ctas_per_sm<V, THREADS, IPT, STAGES>())
 spmv_kernel(SpmvArgs<V> a, CgScalars cg)
@@ -190,7 +224,9 @@ spmv_kernel(SpmvArgs<V> a, CgScalars cg)
     __shared__ uint64_t s_full[STAGES], s_empty[STAGES];
     __shared__ int s_wkey_first[NW], s_wkey_last[NW];
     __shared__ V s_wsum[NW];
-    __shared__ V s_carry[2];                 // tile carry, double-buffered by tile parity
+    __shared__ V s_tcarry[kChainTiles];      // carry-out of each tile of the current chunk
+    __shared__ int s_trow[kChainTiles];      // first row of the tile, or -1 when no row completes in it
+    __shared__ V s_running;                  // carry chained so far (row in progress at the chunk start)
     __shared__ V s_red[THREADS + 32];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -217,7 +253,7 @@ spmv_kernel(SpmvArgs<V> a, CgScalars cg)
     if (tid == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(&s_full[s], 1); mbar_init(&s_empty[s], NW); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        s_carry[0] = 0; s_carry[1] = 0;
+        s_running = 0;
     }
     __syncthreads();
 
@@ -250,15 +286,13 @@ spmv_kernel(SpmvArgs<V> a, CgScalars cg)
         }
     } else {
         // =============================== consumer warps ==========================================
-        const uint64_t pol_keep = l2_policy_evict_last();    // x is gathered ~(nnz/n) times per SpMV
-
         // tile metadata is fetched one tile ahead so its latency hides behind the previous tile
         int2 nxt_lo = make_int2(0, 0), nxt_hi = make_int2(0, 0);
         int nxt_ml = 0;
         if (t0 < t1) { nxt_lo = a.tile_xy[t0]; nxt_hi = a.tile_xy[t0 + 1]; nxt_ml = a.tile_maxlen[t0]; }
 
         for (int t = t0; t < t1; ++t) {
-            const int it = t - t0, s = it % STAGES, par = it & 1;
+            const int it = t - t0, s = it % STAGES, slot = it % kChainTiles;
             const uint32_t parity = (uint32_t)(it / STAGES) & 1u;
             const int2 lo = nxt_lo, hi = nxt_hi;
             const int tile_ml = nxt_ml;
@@ -269,104 +303,77 @@ spmv_kernel(SpmvArgs<V> a, CgScalars cg)
             int *s_col = stage_col(s);
             V *s_val = stage_val(s);
             const int *s_re = stage_ro(s) + (x0 + 1 - rb);   // s_re[i] = end offset of local row i
-            const V *s_prod = s_val + (y0 - yv);               // s_prod[z] = product of local nonzero z
+            const int *pc = s_col + (y0 - yc);                 // pc[z] = column of local nonzero z
+            V *pv = s_val + (y0 - yv);                         // pv[z] = value (or product) of local nonzero z
+
+            if (tid == 0) s_trow[slot] = rows > 0 ? x0 : -1;
 
             mbar_wait(&s_full[s], parity);
 
-            if (!(a.debug_flags & 1)) {
-            // ---- phase A: products in place ----------------------------------------------------
-            // Coalesced and branch-free: 16-byte groups of values and their columns are read with
-            // 128/64-bit shared loads, ALL gathers of the thread are issued before the first product
-            // is formed (MAXIT*EPV independent global loads in flight per thread), and the products
-            // replace the values.  Groups at the tile edges may include nonzeros of the neighbouring
-            // tiles: their products are computed (the column is valid; the slack behind ci is
-            // zero-filled) and never read.
-            {
-                const int nvec = (hi.y - yv + EPV - 1) / EPV;   // 16-byte groups staged
-                constexpr int MAXIT = (SM::VAL_ELEMS / EPV + THREADS - 1) / THREADS;
-                V xv[MAXIT][EPV];
-                const int *cbase = s_col + (yv - yc);
-#pragma unroll
-                for (int q = 0; q < MAXIT; ++q) {
-                    const int g = tid + q * THREADS;           // group index
-                    if (g < nvec) {
-                        int c[EPV];
-                        if constexpr (EPV == 2) {
-                            int2 cc = *reinterpret_cast<const int2 *>(cbase + g * EPV);
-                            c[0] = cc.x; c[1] = cc.y;
-                        } else {
-                            int4 cc = *reinterpret_cast<const int4 *>(cbase + g * EPV);
-                            c[0] = cc.x; c[1] = cc.y; c[2] = cc.z; c[3] = cc.w;
-                        }
-#pragma unroll
-                        for (int e = 0; e < EPV; ++e) xv[q][e] = ldg_hint(a.x + c[e], pol_keep);
-                    }
-                }
-#pragma unroll
-                for (int q = 0; q < MAXIT; ++q) {
-                    const int g = tid + q * THREADS;
-                    if (g < nvec) {
-                        V v[EPV];
-                        ld_vec<V, EPV>(v, s_val + g * EPV);
-#pragma unroll
-                        for (int e = 0; e < EPV; ++e) v[e] *= xv[q][e];
-                        st_vec<V, EPV>(s_val + g * EPV, v);
-                    }
-                }
-            }
-            consumer_sync<THREADS>();
-
-            if (tile_ml <= kRowPathMaxLen) {
-                // ---- phase B, regular tile: one thread per row (two rows interleaved) ----------------
-                // Adjacent lanes own adjacent rows, y is written coalesced, there is no scan.
-                // Pseudo-row `rows` is the trailing part of row hi.x: its sum is the tile carry-out;
-                // row 0 starts from the carry-in.
-                for (int i = tid; i <= rows; i += 2 * THREADS) {
-                    const int iB = i + THREADS;
-                    const bool hasB = iB <= rows;
-                    int begA = (i == 0) ? 0 : s_re[i - 1] - y0;
-                    const int endA = (i == rows) ? nz : s_re[i] - y0;
-                    int begB = 0, endB = 0;
-                    if (hasB) {
-                        begB = s_re[iB - 1] - y0;
-                        endB = (iB == rows) ? nz : s_re[iB] - y0;
-                    }
-                    V xrA = 0, xrB = 0;
+            if (a.debug_flags & 1) {
+                // measurement aid: stream the tile through shared memory and do nothing with it
+                if (tid == 0) s_tcarry[slot] = 0;
+            } else if (tile_ml <= kRowPathMaxLen) {
+                // ---- regular tile: fused thread-per-row path, no barrier --------------------------------
+                // Pseudo-row `rows` is the trailing part of row hi.x: its sum is the tile carry-out.
+                for (int i = tid; i <= rows; i += THREADS) {
+                    const int beg = (i == 0) ? 0 : s_re[i - 1] - y0;
+                    const int end = (i == rows) ? nz : s_re[i] - y0;
+                    V xr = 0;
                     if constexpr (DOT) {
-                        if (i < rows) xrA = __ldg(a.x + x0 + i);
-                        if (hasB && iB < rows) xrB = __ldg(a.x + x0 + iB);
+                        if (i < rows) xr = __ldg(a.x + x0 + i);
                     }
-                    V sumA = (i == 0) ? s_carry[par] : V(0), sumB = 0;
-                    do {
-                        constexpr int UB = 8;
-                        V pa[UB], pb[UB];
-#pragma unroll
-                        for (int j = 0; j < UB; ++j) pa[j] = (begA + j < endA) ? s_prod[begA + j] : V(0);
-#pragma unroll
-                        for (int j = 0; j < UB; ++j) pb[j] = (begB + j < endB) ? s_prod[begB + j] : V(0);
-#pragma unroll
-                        for (int j = 0; j < UB; ++j) sumA += pa[j];
-#pragma unroll
-                        for (int j = 0; j < UB; ++j) sumB += pb[j];
-                        begA += UB; begB += UB;
-                    } while (begA < endA || begB < endB);
+                    const V sum = row_sum<V>(a.x, pc, pv, beg, end);
                     if (i < rows) {
-                        a.y[x0 + i] = sumA;
-                        if constexpr (DOT) dot += sumA * xrA;
+                        a.y[x0 + i] = sum;
+                        if constexpr (DOT) dot += sum * xr;
                     } else {
-                        s_carry[par ^ 1] = sumA;
-                    }
-                    if (hasB) {
-                        if (iB < rows) {
-                            a.y[x0 + iB] = sumB;
-                            if constexpr (DOT) dot += sumB * xrB;
-                        } else {
-                            s_carry[par ^ 1] = sumB;
-                        }
+                        s_tcarry[slot] = sum;
                     }
                 }
             } else {
-                // ---- phase B, general tile: merge-path walk, IPT items per thread -----------------------
+                // ---- general tile, phase A: products in place -----------------------------------------
+                // Coalesced and branch-free: 16-byte groups of values and their columns are read with
+                // 128/64-bit shared loads, all gathers of the thread are issued before the first product
+                // is formed, and the products replace the values.  Groups at the tile edges may include
+                // nonzeros of the neighbouring tiles: their products are computed (the column is valid;
+                // the slack behind ci is zero-filled) and never read.
+                {
+                    const int nvec = (hi.y - yv + EPV - 1) / EPV;   // 16-byte groups staged
+                    constexpr int MAXIT = (SM::VAL_ELEMS / EPV + THREADS - 1) / THREADS;
+                    V xv[MAXIT][EPV];
+                    const int *cbase = s_col + (yv - yc);
+#pragma unroll
+                    for (int q = 0; q < MAXIT; ++q) {
+                        const int g = tid + q * THREADS;           // group index
+                        if (g < nvec) {
+                            int c[EPV];
+                            if constexpr (EPV == 2) {
+                                int2 cc = *reinterpret_cast<const int2 *>(cbase + g * EPV);
+                                c[0] = cc.x; c[1] = cc.y;
+                            } else {
+                                int4 cc = *reinterpret_cast<const int4 *>(cbase + g * EPV);
+                                c[0] = cc.x; c[1] = cc.y; c[2] = cc.z; c[3] = cc.w;
+                            }
+#pragma unroll
+                            for (int e = 0; e < EPV; ++e) xv[q][e] = __ldg(a.x + c[e]);
+                        }
+                    }
+#pragma unroll
+                    for (int q = 0; q < MAXIT; ++q) {
+                        const int g = tid + q * THREADS;
+                        if (g < nvec) {
+                            V v[EPV];
+                            ld_vec<V, EPV>(v, s_val + g * EPV);
+#pragma unroll
+                            for (int e = 0; e < EPV; ++e) v[e] *= xv[q][e];
+                            st_vec<V, EPV>(s_val + g * EPV, v);
+                        }
+                    }
+                }
+                consumer_sync<THREADS>();
+
+                // ---- general tile, phase B: merge-path walk, IPT items per thread -----------------------
                 V *s_y = reinterpret_cast<V *>(s_col);        // row buffer (columns are consumed)
                 const bool y_in_smem = rows <= SM::YBUF_ROWS;
                 const int d0 = min(tid * IPT, items);
@@ -382,15 +389,15 @@ spmv_kernel(SpmvArgs<V> a, CgScalars cg)
                 }
                 int r = r_start;
                 int z = d0 - r;
-                V acc = (tid == 0) ? s_carry[par] : V(0);
+                V acc = 0;
                 int cur_end = s_re[r] - y0;
                 const int n_items = min(IPT, items - d0);
 #pragma unroll
                 for (int i = 0; i < IPT; ++i) {
                     const bool live = i < n_items;
                     const bool is_nz = live && (z < cur_end);
-                    const V pv = s_prod[z];                   // always inside the stage buffer
-                    if (is_nz) { acc += pv; ++z; }
+                    const V pz = pv[z];                       // always inside the stage buffer
+                    if (is_nz) { acc += pz; ++z; }
                     if (live && !is_nz) {
                         if (y_in_smem) s_y[r] = acc; else a.y[x0 + r] = acc;
                         acc = 0;
@@ -429,12 +436,12 @@ spmv_kernel(SpmvArgs<V> a, CgScalars cg)
                 const V sfull = sc + ((wfirst_key == key && wprev_key == key) ? wprev : V(0));
                 V carry_in = __shfl_up_sync(0xffffffffu, sfull, 1);
                 if (lane == 0) carry_in = wprev;
-                if (tid == 0) carry_in = 0;   // the tile carry already seeded thread 0's accumulator
+                if (tid == 0) carry_in = 0;   // the tile's own carry-in is applied by the chain below
                 if (r > r_start) {            // this thread completed row r_start: it owns that entry
                     if (y_in_smem) s_y[r_start] += carry_in;
                     else a.y[x0 + r_start] += carry_in;
                 }
-                if (tid == THREADS - 1) s_carry[par ^ 1] = sfull;   // tile carry-out (row hi.x)
+                if (tid == THREADS - 1) s_tcarry[slot] = sfull;   // tile carry-out (row hi.x)
                 consumer_sync<THREADS>();
 
                 // phase C: coalesced row output (+ dot)
@@ -448,23 +455,47 @@ spmv_kernel(SpmvArgs<V> a, CgScalars cg)
                     for (int i = tid; i < rows; i += THREADS) dot += a.y[x0 + i] * __ldg(a.x + x0 + i);
                 }
             }
-            }  // !(debug_flags & 1)
 
-            // release the stage: generic-proxy writes (products, row buffer) ordered before the next
-            // bulk copy, one arrival per consumer warp
+            // release the stage: generic-proxy accesses ordered before the next bulk copy, one
+            // arrival per consumer warp
             fence_proxy_async();
             __syncwarp();
             if (lane == 0) mbar_arrive(&s_empty[s]);
+
+            // ---- carry chain: every kChainTiles tiles (and after the last one) ------------------------
+            if (slot == kChainTiles - 1 || t == t1 - 1) {
+                consumer_sync<THREADS>();
+                const int cnt = slot + 1;
+                if (tid == 0) {
+                    V run = s_running;
+                    for (int j = 0; j < cnt; ++j) {
+                        const V out = s_tcarry[j];
+                        if (s_trow[j] >= 0) { s_tcarry[j] = run; run = out; }   // run completes row s_trow[j]
+                        else run += out;                                        // row continues through tile j
+                    }
+                    s_running = run;
+                }
+                consumer_sync<THREADS>();
+                for (int j = tid; j < cnt; j += THREADS) {
+                    const int row = s_trow[j];
+                    const V add = s_tcarry[j];
+                    if (row >= 0 && add != V(0)) {
+                        a.y[row] = __ldcg(a.y + row) + add;
+                        if constexpr (DOT) dot += add * __ldg(a.x + row);
+                    }
+                }
+                consumer_sync<THREADS>();
+            }
         }
     }
 
-    __syncthreads();   // all tiles done (producer warp included); s_carry final
+    __syncthreads();   // all tiles done (producer warp included)
 
     // ---- CTA carry-out ---------------------------------------------------------------------------
     if (tid == 0) {
         const bool any = t1 > t0;
         a.carry_row[blockIdx.x] = any ? a.tile_xy[t1].x : a.m;
-        a.carry_val[blockIdx.x] = any ? s_carry[(t1 - t0) & 1] : V(0);
+        a.carry_val[blockIdx.x] = any ? s_running : V(0);
     }
 
     if constexpr (DOT) {
