@@ -59,6 +59,14 @@ int smle_sync(void);                         /* cudaStreamSynchronize on that st
 long long smle_launch_count(void);           /* kernels launched by this library so far */
 int smle_sm_count(void);
 
+/* ---- device buffers ------------------------------------------------------------------------
+ * For callers that keep vectors resident in HBM across calls (is_device_ptr = 1) without
+ * linking the CUDA runtime themselves; the reference has no counterpart (single address space). */
+int smle_malloc(void **dev_ptr, unsigned long long bytes);
+int smle_free(void *dev_ptr);
+int smle_copy_to_device(void *dev_dst, const void *host_src, unsigned long long bytes);
+int smle_copy_to_host(void *host_dst, const void *dev_src, unsigned long long bytes);
+
 /* ---- merge-path partition -----------------------------------------------------------
  * Replaces MergePathSearch (work_2025/spmm/merge_based.hpp:22-44; copies at
  * cpu_spmv.cpp:213-235, cub/thread/thread_search.cuh:48-83) evaluated on the share

@@ -274,6 +274,16 @@ class _Ref(_Backend):
                                                  C.byref(ms), C.byref(it))
         return ms.value, it.value, x
 
+    def read_mtx(self, path):
+        """CooMatrix::InitMarket + CsrMatrix::Init -> (ro, ci, va, num_cols)."""
+        m, n, nnz = _I(0), _I(0), _I(0)
+        fn = self._cg.ref_read_mtx_f64
+        fn.restype = _I
+        fn(str(path).encode(), C.byref(m), C.byref(n), C.byref(nnz), None, None, None)
+        ro, ci, va = self._alloc(m.value, nnz.value, np.float64)
+        fn(str(path).encode(), C.byref(m), C.byref(n), C.byref(nnz), _ptr(ro), _ptr(ci), _ptr(va))
+        return ro, ci, va, n.value
+
     def test_cg_multi(self, ro, ci, va, B, k, max_iters, tol, kernel=MERGE, timing_iters=1):
         """TestCGMultipleRHS (no_pretreatment.hpp:205-256): (min_ms, iters, X)."""
         s, ct = _sfx(va.dtype), _ct(va.dtype)

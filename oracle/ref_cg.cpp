@@ -149,6 +149,18 @@ void ref_merge_path_search(int diagonal, const int *a, int a_len, int b_len, int
 REF_DEFINE(double, f64)
 REF_DEFINE(float, f32)
 
+// CooMatrix::InitMarket (sparse_matrix.h:211-380) + CsrMatrix::Init; two-call protocol:
+// ro == NULL returns the shape only.
+int ref_read_mtx_f64(const char *path, int *m, int *n, int *nnz, int *ro, int *ci, double *va)
+{
+    CooMatrix<double, int> coo;
+    coo.InitMarket(std::string(path), 1.0, false);
+    CsrMatrix<double, int> csr(coo);
+    *m = csr.num_rows; *n = csr.num_cols; *nnz = csr.num_nonzeros;
+    if (ro) copy_out(csr, ro, ci, va);
+    return 0;
+}
+
 void ref_gen_grid2d_shape(int w, int self_loop, int *m, int *n, int *nnz)
 {
     CooMatrix<float, int> coo; coo.InitGrid2d(w, self_loop != 0);

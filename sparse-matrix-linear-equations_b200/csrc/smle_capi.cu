@@ -663,6 +663,41 @@ int smle_sync(void)
 long long smle_launch_count(void) { return g_launches; }
 int smle_sm_count(void) { return ensure_init() ? 0 : g_sms; }
 
+int smle_malloc(void **dev_ptr, unsigned long long bytes)
+{
+    if (!dev_ptr) return fail(SMLE_ERR_ARG, "null pointer");
+    int rc = ensure_init();
+    if (rc) return rc;
+    cudaError_t e = cudaMalloc(dev_ptr, bytes ? bytes : 16);
+    if (e != cudaSuccess) return fail(SMLE_ERR_ALLOC, "cudaMalloc(%llu) failed: %s", bytes, cudaGetErrorString(e));
+    return SMLE_OK;
+}
+
+int smle_free(void *dev_ptr)
+{
+    if (g_stream) cudaStreamSynchronize(g_stream);
+    CU(cudaFree(dev_ptr));
+    return SMLE_OK;
+}
+
+int smle_copy_to_device(void *dev_dst, const void *host_src, unsigned long long bytes)
+{
+    int rc = ensure_init();
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(dev_dst, host_src, bytes, cudaMemcpyHostToDevice, g_stream));
+    CU(cudaStreamSynchronize(g_stream));
+    return SMLE_OK;
+}
+
+int smle_copy_to_host(void *host_dst, const void *dev_src, unsigned long long bytes)
+{
+    int rc = ensure_init();
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(host_dst, dev_src, bytes, cudaMemcpyDeviceToHost, g_stream));
+    CU(cudaStreamSynchronize(g_stream));
+    return SMLE_OK;
+}
+
 int smle_merge_path_partition(const int *row_end, int m, int nnz, int num_parts, int items_per_part,
                               int *out_xy)
 {
