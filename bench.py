@@ -299,7 +299,7 @@ def run_singlecg(args):
                     "h2d_bytes_per_step": L * n * 8, "d2h_bytes_per_step": L * n * 8,
                     "api": "smle_cg_single_f64(host b -> host x), pinned buffers"},
             "gpu_launches": int(launches_all),
-            "roofline": {"bound": "hbm", "kernel": "merge_kernel<double,G=1,VEC=1,DOT> (SpMV + p.Ap)",
+            "roofline": {"bound": "hbm", "kernel": "spmv_kernel<double,256,12,2,DOT> (TMA-staged merge-path SpMV + p.Ap)",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": None, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": k1_bytes,
