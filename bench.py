@@ -25,6 +25,15 @@ from __future__ import annotations
 import argparse
 import json
 import os
+
+# Host cores and OpenMP binding must be settled before any library that embeds an OpenMP runtime
+# is loaded: with OMP_PROC_BIND=true the runtime pins the main thread, after which the affinity
+# mask no longer tells how many cores the process may use.  (The reference wrappers bind with
+# KMP_AFFINITY=granularity=core,scatter; SURVEY.md section 6 measured 8x without binding.)
+HOST_CORES = len(os.sched_getaffinity(0))
+os.environ.setdefault("OMP_PROC_BIND", "true")
+os.environ.setdefault("OMP_PLACES", "cores")
+os.environ.setdefault("OMP_NUM_THREADS", str(HOST_CORES))
 import statistics
 import subprocess
 import sys
@@ -138,7 +147,7 @@ def cpu_backend():
 def cpu_cg_sample(ro, ci, va, b, iters_cap):
     """CGSolveSingle on one vector, capped at iters_cap iterations -> (seconds, iterations)."""
     be, kind = cpu_backend()
-    cores = len(os.sched_getaffinity(0))
+    cores = HOST_CORES
     be.set_threads(cores)
     t0 = time.perf_counter()
     it, _ = be.cg_single(ro, ci, va, b, iters_cap, TOL)
@@ -150,8 +159,6 @@ def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return  # under torchrun only rank 0 runs the CPU arm
-    os.environ.setdefault("OMP_PROC_BIND", "true")
-    os.environ.setdefault("OMP_PLACES", "cores")
     import smle_b200 as S
     ro, ci, va = S.gen_grid3d(GRID, True, 6.0, -1.0)
     n = len(ro) - 1
@@ -310,7 +317,6 @@ def run_singlecg(args):
                                        "frac": cg_iter_bytes(n, nnz, 1) / (iter_ms * 1e-3) / 1e9 / peak}},
         }
         if world == 1 and not args.no_cpu:
-            os.environ.setdefault("OMP_PROC_BIND", "true")
             cap = 40
             cpu_cg_sample(ro, ci, va, stream_all[:n].copy(), 5)
             dt, it, kind, cores = cpu_cg_sample(ro, ci, va, stream_all[:n].copy(), cap)
