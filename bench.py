@@ -30,10 +30,15 @@ import os
 # is loaded: with OMP_PROC_BIND=true the runtime pins the main thread, after which the affinity
 # mask no longer tells how many cores the process may use.  (The reference wrappers bind with
 # KMP_AFFINITY=granularity=core,scatter; SURVEY.md section 6 measured 8x without binding.)
+import sys
+
 HOST_CORES = len(os.sched_getaffinity(0))
-os.environ.setdefault("OMP_PROC_BIND", "true")
-os.environ.setdefault("OMP_PLACES", "cores")
-os.environ.setdefault("OMP_NUM_THREADS", str(HOST_CORES))
+if int(os.environ.get("WORLD_SIZE", "1")) == 1 or "reference" in sys.argv:
+    # only the process that times the CPU reference binds its OpenMP team; under torchrun the
+    # ranks must not all pin their launch threads to core 0
+    os.environ.setdefault("OMP_PROC_BIND", "true")
+    os.environ.setdefault("OMP_PLACES", "cores")
+    os.environ["OMP_NUM_THREADS"] = str(HOST_CORES)
 import statistics
 import subprocess
 import sys

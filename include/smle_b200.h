@@ -130,6 +130,31 @@ int smle_cg_run_fixed_f64(smle_csr_t a, const double *B, double *X, int k, int i
 int smle_cg_profile_f64(smle_csr_t a, const double *B, double *X, int k, int iters,
                         float *ms_per_kernel);
 
+/* ---- row-partitioned CG over NVLink peer memory (one process per GPU) -----------------------
+ * Net-new relative to the reference (which has no distributed code); semantics of the solve are
+ * CGSolveSingle's (single_strategy.hpp:105-170) on the global system.  The partition is cut at
+ * the reference's merge-path coordinates: part g owns rows [x_g, x_{g+1}) with
+ * x_g = MergePathSearch(min(g*ceil((m+nnz)/G), m+nnz)).x (smle_merge_path_partition).
+ *   local_a      this rank's rows; columns remapped to [0,n_local) own | [n_local,n_local+n_halo) halo
+ *   send_off     world+1 offsets into send_idx: entries this rank pushes to each peer
+ *   send_idx     local row indices of those entries (grouped by peer, in the peer's halo order)
+ *   send_dst     per peer: element offset in THAT peer's extended vector where the group lands
+ *   needs_from   per peer: 1 when this rank receives halo entries from it
+ * smle_dist_ipc_handle / smle_dist_connect exchange the 64-byte CUDA IPC handles of the per-rank
+ * communication buffers (the caller moves the bytes, e.g. torch.distributed.all_gather).
+ * smle_dist_spmv_f64 and smle_dist_cg_f64 are collective over the partition; vectors are device
+ * pointers to this rank's rows.  Halo pushes and the dot-product all-reduce are done by the
+ * kernels themselves through peer stores and mailbox flags -- no NCCL on the data path. */
+typedef struct smle_dist_s *smle_dist_t;
+int smle_dist_create(smle_dist_t *out, smle_csr_t local_a, int rank, int world, int n_local, int n_halo,
+                     const int *send_off, const int *send_idx, const int *send_dst, const int *needs_from);
+int smle_dist_ipc_handle(smle_dist_t d, unsigned char *out64);
+int smle_dist_connect(smle_dist_t d, const unsigned char *all_handles);
+int smle_dist_spmv_f64(smle_dist_t d, const double *x_local_dev, double *y_local_dev);
+int smle_dist_cg_f64(smle_dist_t d, const double *b_local_dev, double *x_local_dev, int max_iters, double tol,
+                     int *iters_out, double *final_rel_res);
+void smle_dist_destroy(smle_dist_t d);
+
 /* ---- matrix / RHS generators (host side) -------------------------------------------------
  * CSR output identical to the reference generator followed by CsrMatrix::Init
  * (sparse_matrix.h:668-733): InitGrid2d :458-527, InitGrid3d :533-623, InitWheel :417-450,

@@ -19,6 +19,7 @@
 #include "smle_cg.cuh"
 #include "smle_merge.cuh"
 #include "smle_spmv.cuh"
+#include "smle_dist.cuh"
 
 using namespace smle;
 
@@ -435,16 +436,16 @@ CgScalars make_scalars(CgWorkspace &w, int k)
 }
 
 template <int G, int VEC>
-int launch_vec_t(int which, const CgVecArgs &va, const CgScalars &cg, int max_iters, double tol, int grid)
+int launch_vec_t(int which, const CgVecArgs &va, const CgScalars &cg, int max_iters, double tol, int grid, int seq_base)
 {
-    if (which == 0) cg_init_kernel<G, VEC><<<grid, kThreads, 0, g_stream>>>(va, cg, max_iters, tol);
+    if (which == 0) cg_init_kernel<G, VEC><<<grid, kThreads, 0, g_stream>>>(va, cg, max_iters, tol, seq_base);
     else if (which == 1) cg_update_r_kernel<G, VEC><<<grid, kThreads, 0, g_stream>>>(va, cg);
     else cg_update_xp_kernel<G, VEC><<<grid, kThreads, 0, g_stream>>>(va, cg);
     ++g_launches;
     return check_launch("cg vector kernel");
 }
 
-int launch_vec(int which, const CgVecArgs &va, const CgScalars &cg, int max_iters = 0, double tol = 0.0)
+int launch_vec(int which, const CgVecArgs &va, const CgScalars &cg, int max_iters = 0, double tol = 0.0, int seq_base = 0)
 {
     if (va.k == 1 && which != 0 && getenv("SMLE_VEC_GENERIC") == nullptr) {
         // single right-hand side: 128-bit, unrolled kernels with L2 eviction priorities
@@ -464,7 +465,7 @@ int launch_vec(int which, const CgVecArgs &va, const CgScalars &cg, int max_iter
     long long want = ((long long)va.n + W - 1) / W;
     int grid = (int)(want < (long long)g_sms * 8 ? want : (long long)g_sms * 8);
     if (grid < 1) grid = 1;
-#define SMLE_CASE(g, v) if (G == g && VEC == v) return launch_vec_t<g, v>(which, va, cg, max_iters, tol, grid);
+#define SMLE_CASE(g, v) if (G == g && VEC == v) return launch_vec_t<g, v>(which, va, cg, max_iters, tol, grid, seq_base);
     SMLE_CASE(1, 1) SMLE_CASE(2, 1) SMLE_CASE(4, 1) SMLE_CASE(8, 1) SMLE_CASE(16, 1) SMLE_CASE(32, 1)
     SMLE_CASE(1, 2) SMLE_CASE(2, 2) SMLE_CASE(4, 2) SMLE_CASE(8, 2) SMLE_CASE(16, 2) SMLE_CASE(32, 2)
 #undef SMLE_CASE
@@ -860,6 +861,254 @@ int smle_cg_profile_f64(smle_csr_t a, const double *B, double *X, int k, int ite
     }
     for (auto &ev1 : ev) cudaEventDestroy(ev1);
     return rc;
+}
+
+} // extern "C"
+
+// =========================================================================================
+// row-partitioned CG over NVLink peer memory (one process per GPU; smle_dist.cuh)
+// =========================================================================================
+struct smle_dist_s {
+    smle_csr_t a = nullptr;            // local rows, columns remapped to [own | halo]
+    int rank = 0, world = 1, n_local = 0, n_halo = 0;
+    unsigned char *comm = nullptr;     // [DistBlock (4 KB) | p vector (n_local + n_halo doubles)]
+    void *peer_base[kMaxRanks] = {};
+    int *send_idx = nullptr;
+    unsigned int *ticket = nullptr;
+    DistCtl ctl;
+    int seq_base = 0;
+    cudaGraphExec_t graph = nullptr;
+    bool connected = false;
+};
+
+namespace {
+
+double *dist_p(smle_dist_t d) { return (double *)(d->comm + kDistCtlBytes); }
+
+int dist_launch_iteration(smle_dist_t d, const CgVecArgs &va, const CgScalars &cg)
+{
+    // K1 local SpMV + local p.Ap  ->  post  ->  K2  ->  post  ->  K3  ->  halo push
+    int rc = launch_merge<double, true>(d->a, va.P, va.AP, 1, cg);
+    if (rc) return rc;
+    dist_post_kernel<<<1, 32, 0, g_stream>>>(d->ctl, 0, cg.pAp, cg.ctrl);
+    long long want = ((long long)(va.n >> 1) + kThreads * kVecUnroll - 1) / (kThreads * kVecUnroll);
+    int grid = (int)(want < (long long)g_sms * 2 ? want : (long long)g_sms * 2);
+    if (grid < 1) grid = 1;
+    cg1d_update_r_kernel<<<grid, kThreads, 0, g_stream>>>(va, cg, d->ctl);
+    dist_post_kernel<<<1, 32, 0, g_stream>>>(d->ctl, 1, cg.rs_new, cg.ctrl);
+    cg1d_update_xp_kernel<<<grid, kThreads, 0, g_stream>>>(va, cg, d->ctl, 0);
+    int total = d->ctl.send_off[d->world];
+    int pgrid = (total + kThreads - 1) / kThreads;
+    if (pgrid < 1) pgrid = 1;
+    if (pgrid > g_sms) pgrid = g_sms;
+    dist_halo_push_kernel<<<pgrid, kThreads, 0, g_stream>>>(d->ctl, va.P, cg.ctrl);
+    g_launches += 5;
+    return check_launch("distributed CG iteration");
+}
+
+} // namespace
+
+extern "C" {
+
+int smle_dist_create(smle_dist_t *out, smle_csr_t local_a, int rank, int world, int n_local, int n_halo,
+                     const int *send_off, const int *send_idx, const int *send_dst, const int *needs_from)
+{
+    if (!out || !local_a || world < 1 || world > kMaxRanks || rank < 0 || rank >= world || n_local < 0 || n_halo < 0 ||
+        !send_off || !send_dst || !needs_from)
+        return fail(SMLE_ERR_ARG, "smle_dist_create: bad argument (world must be 1..%d)", kMaxRanks);
+    if (local_a->vbytes != 8 || local_a->m != n_local || local_a->n != n_local + n_halo)
+        return fail(SMLE_ERR_ARG, "local matrix must be fp64 with n_local rows and n_local+n_halo columns");
+    int rc = ensure_init();
+    if (rc) return rc;
+    smle_dist_s *d = new (std::nothrow) smle_dist_s();
+    if (!d) return fail(SMLE_ERR_ALLOC, "out of host memory");
+    d->a = local_a; d->rank = rank; d->world = world; d->n_local = n_local; d->n_halo = n_halo;
+    size_t bytes = kDistCtlBytes + sizeof(double) * ((size_t)n_local + n_halo + 2);
+    CU(cudaMalloc(&d->comm, bytes));
+    CU(cudaMemsetAsync(d->comm, 0, bytes, g_stream));
+    int total = send_off[world];
+    CU(cudaMalloc(&d->send_idx, sizeof(int) * (size_t)(total > 0 ? total : 1)));
+    if (total > 0) CU(cudaMemcpyAsync(d->send_idx, send_idx, sizeof(int) * (size_t)total, cudaMemcpyHostToDevice, g_stream));
+    CU(cudaMalloc(&d->ticket, sizeof(unsigned int) * 4));
+    CU(cudaMemsetAsync(d->ticket, 0, sizeof(unsigned int) * 4, g_stream));
+    CU(cudaStreamSynchronize(g_stream));
+    DistCtl &c = d->ctl;
+    memset(&c, 0, sizeof(c));
+    c.rank = rank; c.world = world;
+    c.self = (DistBlock *)d->comm;
+    c.send_idx = d->send_idx;
+    for (int q = 0; q <= world; ++q) c.send_off[q] = send_off[q];
+    for (int q = 0; q < world; ++q) { c.send_dst[q] = send_dst[q]; c.needs_from[q] = needs_from[q]; }
+    c.ticket = d->ticket;
+    c.peer[rank] = c.self;
+    c.peer_p[rank] = dist_p(d);
+    d->peer_base[rank] = d->comm;
+    d->connected = (world == 1);
+    *out = d;
+    return SMLE_OK;
+}
+
+int smle_dist_ipc_handle(smle_dist_t d, unsigned char *out64)
+{
+    if (!d || !out64) return fail(SMLE_ERR_ARG, "bad argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    cudaIpcMemHandle_t h;
+    CU(cudaIpcGetMemHandle(&h, d->comm));
+    memcpy(out64, &h, 64);
+    return SMLE_OK;
+}
+
+int smle_dist_connect(smle_dist_t d, const unsigned char *all_handles)
+{
+    if (!d || !all_handles) return fail(SMLE_ERR_ARG, "bad argument");
+    for (int q = 0; q < d->world; ++q) {
+        if (q == d->rank) continue;
+        cudaIpcMemHandle_t h;
+        memcpy(&h, all_handles + (size_t)q * 64, 64);
+        void *base = nullptr;
+        cudaError_t e = cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) return fail(SMLE_ERR_COMM, "cudaIpcOpenMemHandle(rank %d) failed: %s", q, cudaGetErrorString(e));
+        d->peer_base[q] = base;
+        d->ctl.peer[q] = (DistBlock *)base;
+        d->ctl.peer_p[q] = (double *)((unsigned char *)base + kDistCtlBytes);
+    }
+    d->connected = true;
+    return SMLE_OK;
+}
+
+void smle_dist_destroy(smle_dist_t d)
+{
+    if (!d) return;
+    if (g_stream) cudaStreamSynchronize(g_stream);
+    if (d->graph) cudaGraphExecDestroy(d->graph);
+    for (int q = 0; q < d->world; ++q)
+        if (q != d->rank && d->peer_base[q]) cudaIpcCloseMemHandle(d->peer_base[q]);
+    cudaFree(d->comm); cudaFree(d->send_idx); cudaFree(d->ticket);
+    delete d;
+}
+
+// y_local = (A x)_local : pushes/receives the halo of x, then the local merge-path SpMV.
+// Collective: every rank of the partition must call it.
+int smle_dist_spmv_f64(smle_dist_t d, const double *x_local_dev, double *y_local_dev)
+{
+    if (!d || !x_local_dev || !y_local_dev) return fail(SMLE_ERR_ARG, "bad argument");
+    if (!d->connected) return fail(SMLE_ERR_COMM, "smle_dist_connect has not been called");
+    int rc = ensure_workspace(d->a, 1, 0);
+    if (rc) return rc;
+    CgWorkspace &w = d->a->ws;
+    int ctrl[CTRL_WORDS] = {0, 0, 0, 1, 0, d->seq_base, 0, 0};
+    CU(cudaMemcpyAsync(w.ctrl, ctrl, sizeof(ctrl), cudaMemcpyHostToDevice, g_stream));
+    CU(cudaMemcpyAsync(dist_p(d), x_local_dev, sizeof(double) * (size_t)d->n_local, cudaMemcpyDeviceToDevice, g_stream));
+    int total = d->ctl.send_off[d->world];
+    int pgrid = (total + kThreads - 1) / kThreads;
+    if (pgrid < 1) pgrid = 1;
+    if (pgrid > g_sms) pgrid = g_sms;
+    dist_halo_push_kernel<<<pgrid, kThreads, 0, g_stream>>>(d->ctl, dist_p(d), w.ctrl);
+    ++g_launches;
+    rc = check_launch("dist_halo_push_kernel");
+    if (rc) return rc;
+    d->seq_base += 2;
+    CgScalars none = {};
+    return launch_merge<double, false>(d->a, dist_p(d), y_local_dev, 1, none);
+}
+
+// Row-partitioned CGSolveSingle (single_strategy.hpp:105-170 semantics on the global system).
+// b_local / x_local: this rank's rows, device pointers.  Collective over the partition.
+int smle_dist_cg_f64(smle_dist_t d, const double *b_local_dev, double *x_local_dev, int max_iters, double tol,
+                     int *iters_out, double *final_rel_res)
+{
+    if (!d || !b_local_dev || !x_local_dev) return fail(SMLE_ERR_ARG, "bad argument");
+    if (!d->connected) return fail(SMLE_ERR_COMM, "smle_dist_connect has not been called");
+    smle_csr_t a = d->a;
+    int rc = ensure_workspace(a, 1, 0);
+    if (!rc) rc = ensure_scratch(a, 1);
+    if (rc) return rc;
+    CgWorkspace &w = a->ws;
+    CgScalars cg = make_scalars(w, 1);
+    CgVecArgs va;
+    va.B = b_local_dev; va.X = w.Xd; va.R = w.R; va.P = dist_p(d); va.AP = w.AP;
+    va.n = d->n_local; va.k = 1; va.part = w.part; va.ticket = a->ticket + 1;
+
+    // init: x = 0, r = p = b, local b.b -> all-reduce -> rs_old, bnorm; first halo push
+    rc = launch_vec(0, va, cg, max_iters, tol, d->seq_base);
+    if (rc) return rc;
+    dist_post_kernel<<<1, 32, 0, g_stream>>>(d->ctl, 2, cg.rs_old, cg.ctrl);
+    cg1d_update_xp_kernel<<<1, kThreads, 0, g_stream>>>(va, cg, d->ctl, 1);
+    {
+        int total = d->ctl.send_off[d->world];
+        int pgrid = (total + kThreads - 1) / kThreads;
+        if (pgrid < 1) pgrid = 1;
+        if (pgrid > g_sms) pgrid = g_sms;
+        dist_halo_push_kernel<<<pgrid, kThreads, 0, g_stream>>>(d->ctl, va.P, cg.ctrl);
+    }
+    g_launches += 3;
+    rc = check_launch("distributed CG init");
+    if (rc) return rc;
+
+    const bool use_graph = getenv("SMLE_NO_GRAPH") == nullptr;
+    if (use_graph && !d->graph) {
+        rc = launch_merge<double, true>(a, va.P, va.AP, 1, cg, /*dry=*/true);
+        if (rc) return rc;
+        cudaGraph_t graph;
+        CU(cudaStreamBeginCapture(g_stream, cudaStreamCaptureModeThreadLocal));
+        for (int i = 0; i < kGraphIters && !rc; ++i) rc = dist_launch_iteration(d, va, cg);
+        cudaError_t e = cudaStreamEndCapture(g_stream, &graph);
+        g_launches -= 6LL * kGraphIters;
+        if (rc) return rc;
+        if (e != cudaSuccess) return fail(SMLE_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(e));
+        e = cudaGraphInstantiate(&d->graph, graph, 0);
+        cudaGraphDestroy(graph);
+        if (e != cudaSuccess) return fail(SMLE_ERR_CUDA, "graph instantiate failed: %s", cudaGetErrorString(e));
+    }
+    const int batch = use_graph ? kGraphIters : 4;
+    cudaEvent_t ev[2];
+    CU(cudaEventCreateWithFlags(&ev[0], cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&ev[1], cudaEventDisableTiming));
+    auto submit = [&](int slot) -> int {
+        if (use_graph) {
+            CU(cudaGraphLaunch(d->graph, g_stream));
+            g_launches += 6LL * batch;
+        } else {
+            for (int i = 0; i < batch; ++i) {
+                int r2 = dist_launch_iteration(d, va, cg);
+                if (r2) return r2;
+            }
+        }
+        CU(cudaMemcpyAsync(w.ctrl_host + slot * CTRL_WORDS, w.ctrl, sizeof(int) * CTRL_WORDS, cudaMemcpyDeviceToHost, g_stream));
+        CU(cudaEventRecord(ev[slot], g_stream));
+        return SMLE_OK;
+    };
+    if (max_iters > 0) {
+        int launched = 0, j = 0;
+        rc = submit(0);
+        launched += batch;
+        while (!rc) {
+            const bool more = launched < max_iters;
+            if (more) {
+                rc = submit((j + 1) & 1);
+                launched += batch;
+                if (rc) break;
+            }
+            CU(cudaEventSynchronize(ev[j & 1]));
+            if (w.ctrl_host[(j & 1) * CTRL_WORDS + CTRL_STOP] || !more) break;
+            ++j;
+        }
+    }
+    cudaEventDestroy(ev[0]);
+    cudaEventDestroy(ev[1]);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(x_local_dev, w.Xd, sizeof(double) * (size_t)d->n_local, cudaMemcpyDeviceToDevice, g_stream));
+    CU(cudaMemcpyAsync(w.ctrl_host, w.ctrl, sizeof(int) * CTRL_WORDS, cudaMemcpyDeviceToHost, g_stream));
+    CU(cudaMemcpyAsync(w.ctrl_host + CTRL_WORDS, cg.last_rel, sizeof(double), cudaMemcpyDeviceToHost, g_stream));
+    int err = 0;
+    CU(cudaMemcpyAsync(&err, &d->ctl.self->error, sizeof(int), cudaMemcpyDeviceToHost, g_stream));
+    CU(cudaStreamSynchronize(g_stream));
+    const int iters = w.ctrl_host[CTRL_ITER];
+    d->seq_base += iters + 2;
+    if (iters_out) *iters_out = iters;
+    if (final_rel_res) memcpy(final_rel_res, w.ctrl_host + CTRL_WORDS, sizeof(double));
+    if (err) return fail(SMLE_ERR_COMM, "a peer did not answer (spin-wait timeout)");
+    return SMLE_OK;
 }
 
 } // extern "C"

@@ -66,7 +66,7 @@ __device__ __forceinline__ void publish_partials(double (&s)[VEC], int cb, int k
 // ---------------------------------------------------------------------------------------
 template <int G, int VEC>
 __global__ void __launch_bounds__(kThreads)
-cg_init_kernel(CgVecArgs a, CgScalars cg, int max_iters, double tol)
+cg_init_kernel(CgVecArgs a, CgScalars cg, int max_iters, double tol, int seq_base)
 {
     constexpr int W = kThreads / G, KB = G * VEC;
     __shared__ double s_w[kWarps][KB];
@@ -107,6 +107,7 @@ cg_init_kernel(CgVecArgs a, CgScalars cg, int max_iters, double tol)
         cg.ctrl[CTRL_HALT] = max_iters <= 0 ? 1 : 0;
         cg.ctrl[CTRL_MAX_ITERS] = max_iters;
         cg.ctrl[CTRL_NCONV] = 0;
+        cg.ctrl[CTRL_SEQ_BASE] = seq_base;
         *cg.last_rel = 0.0;
         *cg.tol = tol;
     }

@@ -15,6 +15,7 @@ constexpr int kWarps = kThreads / 32;
 // reads these on the host except through one async copy of `ctrl` per graph batch.
 // ---------------------------------------------------------------------------------------
 enum CtrlSlot { CTRL_ITER = 0, CTRL_STOP = 1, CTRL_HALT = 2, CTRL_MAX_ITERS = 3, CTRL_NCONV = 4,
+                CTRL_SEQ_BASE = 5,   // multi-GPU: sequence numbers of this solve start here
                 CTRL_WORDS = 8 };
 
 struct CgScalars {

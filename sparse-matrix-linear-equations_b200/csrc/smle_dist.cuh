@@ -1,0 +1,269 @@
+// smle_dist.cuh -- row-partitioned single-RHS CG over NVLink peer memory.
+//
+// The reference has no distributed code; this is the B200-native extension north_star asks for:
+// one process per GPU, contiguous row blocks cut at the reference's merge-path coordinates
+// (MergePathSearch on diagonals g*ceil((m+nnz)/G)), and NO library collective on the data path:
+//
+//   * halo exchange: after p is updated, every rank PUSHES the entries its neighbours need
+//     straight into the halo tail of their p vector (peer pointers from CUDA IPC, stores over
+//     NVLink), fences, publishes a sequence number in the neighbour's memory, and waits for
+//     its own incoming sequence numbers;
+//   * dot products: every rank posts its partial sum into a mailbox slot in EVERY peer's memory;
+//     the consuming kernel spins on its local mailbox and adds the G values in rank order, so
+//     all ranks obtain bit-identical alpha / beta / convergence decisions with one NVLink
+//     write latency instead of a collective call.
+//
+// Sequence numbers are derived from the device-resident iteration counter, so the whole
+// iteration (6 launches) replays from one CUDA graph.  Mailbox slots are double-buffered by
+// iteration parity; the reduction dependency chain keeps ranks within one step of each other,
+// which makes the reuse safe.
+#pragma once
+#include "smle_cg.cuh"
+#include "smle_common.cuh"
+
+namespace smle {
+
+constexpr int kMaxRanks = 8;
+constexpr int kMailKinds = 3;                 // 0: p.Ap   1: r.r   2: b.b (initialisation)
+constexpr size_t kDistCtlBytes = 4096;        // control block in front of the p vector
+
+// layout of the control block (identical on every rank; peers address it through IPC)
+struct DistBlock {
+    unsigned long long halo_seq[kMaxRanks];                           // written by peer q: halo of step seq has landed
+    unsigned long long mail_seq[kMailKinds * 2 * kMaxRanks];
+    double mail_val[kMailKinds * 2 * kMaxRanks];
+    int error;                                                         // spin-wait timeout seen
+};
+static_assert(sizeof(DistBlock) <= kDistCtlBytes, "control block too large");
+
+struct DistCtl {
+    int rank, world;
+    DistBlock *self;                    // local control block
+    DistBlock *peer[kMaxRanks];         // every rank's control block (peer[rank] == self)
+    double *peer_p[kMaxRanks];          // every rank's extended p vector [n_local + n_halo]
+    const int *send_idx;                // local indices of the entries to push, grouped by peer
+    int send_off[kMaxRanks + 1];        // group boundaries
+    int send_dst[kMaxRanks];            // element offset in the peer's p vector where my group lands
+    int needs_from[kMaxRanks];          // 1 when this rank receives halo entries from peer q
+    unsigned int *ticket;
+};
+
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p)
+{
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v)
+{
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+__device__ __forceinline__ bool dist_spin(const unsigned long long *flag, unsigned long long want, int *error)
+{
+    long long spins = 0;
+    while (ld_acquire_sys(flag) < want) {
+        if (++spins > (1ll << 28)) {   // ~ seconds: a peer died or the launch order is broken
+            *error = 1;
+            return false;
+        }
+    }
+    return true;
+}
+
+// sum of the `kind` mailbox over ranks in rank order (called by one thread)
+__device__ __forceinline__ double dist_wait_sum(const DistCtl &d, int kind, int parity, unsigned long long seq)
+{
+    double s = 0.0;
+    for (int q = 0; q < d.world; ++q) {
+        const int idx = (kind * 2 + parity) * kMaxRanks + q;
+        dist_spin(&d.self->mail_seq[idx], seq, &d.self->error);
+        s += *(volatile double *)&d.self->mail_val[idx];
+    }
+    return s;
+}
+
+// One warp: lane q posts this rank's partial `*value` into peer q's mailbox.
+__global__ void dist_post_kernel(DistCtl d, int kind, const double *value, const int *ctrl)
+{
+    if (kind != 2 && ctrl[CTRL_STOP]) return;
+    const int it = ctrl[CTRL_ITER];
+    const unsigned long long seq = (unsigned long long)ctrl[CTRL_SEQ_BASE] + (kind == 2 ? 1ull : (unsigned long long)it + 1ull);
+    const int parity = kind == 2 ? 0 : (it & 1);
+    const int q = threadIdx.x;
+    if (q < d.world) {
+        const int idx = (kind * 2 + parity) * kMaxRanks + d.rank;
+        *(volatile double *)&d.peer[q]->mail_val[idx] = *value;
+        __threadfence_system();
+        st_release_sys(&d.peer[q]->mail_seq[idx], seq);
+    }
+}
+
+// K2 (distributed): alpha from the all-reduced p.Ap, r -= alpha*Ap, local r.r -> cg.rs_new[0]
+__global__ void __launch_bounds__(kThreads)
+cg1d_update_r_kernel(CgVecArgs a, CgScalars cg, DistCtl d)
+{
+    __shared__ double s_red[kThreads];
+    __shared__ double s_alpha;
+    if (cg.ctrl[CTRL_STOP]) return;
+    const int tid = threadIdx.x;
+    if (tid == 0) {
+        const int it = cg.ctrl[CTRL_ITER];
+        const double pAp = dist_wait_sum(d, 0, it & 1, (unsigned long long)cg.ctrl[CTRL_SEQ_BASE] + (unsigned long long)it + 1ull);
+        s_alpha = cg.rs_old[0] / pAp;
+        if (blockIdx.x == 0) cg.alpha[0] = s_alpha;
+    }
+    __syncthreads();
+    const uint64_t pol_first = make_policy_evict_first(), pol_last = make_policy_evict_last();
+    const double na = -s_alpha;
+    const long long n2 = a.n >> 1;
+    const long long stride = (long long)gridDim.x * kThreads;
+    double s = 0.0;
+    for (long long i = (long long)blockIdx.x * kThreads + tid; i < n2; i += stride * kVecUnroll) {
+        double2 r[kVecUnroll], ap[kVecUnroll];
+#pragma unroll
+        for (int u = 0; u < kVecUnroll; ++u) {
+            const long long j = i + u * stride;
+            if (j < n2) {
+                r[u] = ld_f64x2_hint(a.R + 2 * j, pol_last);
+                ap[u] = ld_f64x2_hint(a.AP + 2 * j, pol_first);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < kVecUnroll; ++u) {
+            const long long j = i + u * stride;
+            if (j < n2) {
+                r[u].x += na * ap[u].x;
+                r[u].y += na * ap[u].y;
+                s += r[u].x * r[u].x;
+                s += r[u].y * r[u].y;
+                st_f64x2_hint(a.R + 2 * j, r[u], pol_last);
+            }
+        }
+    }
+    if ((a.n & 1) && blockIdx.x == 0 && tid == 0) {
+        const int j = a.n - 1;
+        double r = a.R[j] + na * a.AP[j];
+        a.R[j] = r;
+        s += r * r;
+    }
+#pragma unroll
+    for (int dd = 16; dd > 0; dd >>= 1) s += __shfl_xor_sync(0xffffffffu, s, dd);
+    if ((tid & 31) == 0) s_red[tid >> 5] = s;
+    __syncthreads();
+    if (tid == 0) {
+        double t = 0;
+        for (int i = 0; i < kWarps; ++i) t += s_red[i];
+        a.part[blockIdx.x] = t;
+    }
+    if (!last_cta_election(a.ticket, gridDim.x)) return;
+    cta_reduce_columns<double>(a.part, nullptr, gridDim.x, 1, cg.rs_new, s_red);   // local r.r
+}
+
+// K3 (distributed).  mode 0: beta / convergence from the all-reduced r.r, x += alpha p,
+// p = r + beta p; the last CTA advances the iteration state.  mode 1 (after cg_init_kernel):
+// only turns the all-reduced b.b into rs_old / bnorm.
+__global__ void __launch_bounds__(kThreads)
+cg1d_update_xp_kernel(CgVecArgs a, CgScalars cg, DistCtl d, int mode)
+{
+    __shared__ double s_rr, s_beta;
+    __shared__ int s_final;
+    if (cg.ctrl[CTRL_STOP]) return;
+    const int tid = threadIdx.x;
+    if (tid == 0) {
+        const int it = cg.ctrl[CTRL_ITER];
+        if (mode == 1) {
+            s_rr = dist_wait_sum(d, 2, 0, (unsigned long long)cg.ctrl[CTRL_SEQ_BASE] + 1ull);
+            s_beta = 0.0;
+            s_final = 0;
+        } else {
+            const double rr = dist_wait_sum(d, 1, it & 1, (unsigned long long)cg.ctrl[CTRL_SEQ_BASE] + (unsigned long long)it + 1ull);
+            const double rel = sqrt(rr) / cg.bnorm[0];
+            s_rr = rr;
+            s_beta = rr / cg.rs_old[0];
+            s_final = (rel < *cg.tol) || (it + 1 >= cg.ctrl[CTRL_MAX_ITERS]);
+        }
+    }
+    __syncthreads();
+    if (mode == 0) {
+        const bool final_iter = s_final != 0;
+        const uint64_t pol_first = make_policy_evict_first(), pol_last = make_policy_evict_last();
+        const double al = cg.alpha[0], be = s_beta;
+        const long long n2 = a.n >> 1;
+        const long long stride = (long long)gridDim.x * kThreads;
+        for (long long i = (long long)blockIdx.x * kThreads + tid; i < n2; i += stride * kVecUnroll) {
+            double2 x[kVecUnroll], p[kVecUnroll], r[kVecUnroll];
+#pragma unroll
+            for (int u = 0; u < kVecUnroll; ++u) {
+                const long long j = i + u * stride;
+                if (j < n2) {
+                    x[u] = ld_f64x2_hint(a.X + 2 * j, pol_first);
+                    p[u] = ld_f64x2_hint(a.P + 2 * j, pol_last);
+                    if (!final_iter) r[u] = ld_f64x2_hint(a.R + 2 * j, pol_last);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < kVecUnroll; ++u) {
+                const long long j = i + u * stride;
+                if (j < n2) {
+                    x[u].x += al * p[u].x;
+                    x[u].y += al * p[u].y;
+                    st_f64x2_hint(a.X + 2 * j, x[u], pol_first);
+                    if (!final_iter) {
+                        p[u].x = r[u].x + be * p[u].x;
+                        p[u].y = r[u].y + be * p[u].y;
+                        st_f64x2_hint(a.P + 2 * j, p[u], pol_last);
+                    }
+                }
+            }
+        }
+        if ((a.n & 1) && blockIdx.x == 0 && tid == 0) {
+            const int j = a.n - 1;
+            const double pj = a.P[j];
+            a.X[j] += al * pj;
+            if (!final_iter) a.P[j] = a.R[j] + be * pj;
+        }
+    }
+    if (!last_cta_election(a.ticket, gridDim.x)) return;
+    if (tid == 0) {
+        if (mode == 1) {
+            const double nb = sqrt(s_rr);
+            cg.rs_old[0] = s_rr;
+            cg.bnorm[0] = nb == 0.0 ? 1.0 : nb;
+        } else {
+            const int it = cg.ctrl[CTRL_ITER];
+            const double rel = sqrt(s_rr) / cg.bnorm[0];
+            if (cg.hist && it < cg.hist_cap) cg.hist[it] = rel;
+            *cg.last_rel = rel;
+            cg.rs_new[0] = s_rr;
+            cg.rs_old[0] = s_rr;
+            cg.ctrl[CTRL_ITER] = it + 1;
+            if (s_final) cg.ctrl[CTRL_STOP] = 1;
+        }
+    }
+}
+
+// Halo push: P[send_idx] -> the halo tail of each neighbour's p vector, then sequence numbers,
+// then wait for the neighbours' pushes.  When it returns, the next SpMV can start.
+__global__ void __launch_bounds__(kThreads)
+dist_halo_push_kernel(DistCtl d, const double *__restrict__ P, const int *ctrl)
+{
+    if (ctrl[CTRL_STOP]) return;
+    const unsigned long long seq = (unsigned long long)ctrl[CTRL_SEQ_BASE] + (unsigned long long)ctrl[CTRL_ITER] + 1ull;   // step the halo is for
+    const int total = d.send_off[d.world];
+    for (int i = blockIdx.x * kThreads + threadIdx.x; i < total; i += gridDim.x * kThreads) {
+        int q = 0;
+        while (i >= d.send_off[q + 1]) ++q;
+        d.peer_p[q][d.send_dst[q] + (i - d.send_off[q])] = P[d.send_idx[i]];
+    }
+    __threadfence_system();
+    if (!last_cta_election(d.ticket, gridDim.x)) return;
+    const int q = threadIdx.x;
+    if (q < d.world && q != d.rank) {
+        if (d.send_off[q + 1] > d.send_off[q]) st_release_sys(&d.peer[q]->halo_seq[d.rank], seq);
+        if (d.needs_from[q]) dist_spin(&d.self->halo_seq[q], seq, &d.self->error);
+    }
+}
+
+} // namespace smle
