@@ -35,6 +35,7 @@ int g_device = -1;
 int g_sms = 0;
 long long g_launches = 0;
 long long *g_timing = nullptr;   // device debug counters (SMLE_TIMING builds)
+const void *g_spmv_dist = nullptr;   // device DistCtl of the row-partitioned solve being launched
 
 int fail(int code, const char *fmt, ...)
 {
@@ -270,6 +271,7 @@ int launch_spmv_t(smle_csr_t a, const V *x, V *y, const CgScalars &cg, bool dry)
     args.dot_part = (V *)a->dot_part; args.fix_part = (V *)a->fix_part;
     args.ticket = a->ticket;
     args.timing = g_timing;
+    args.dist = (const DistCtl *)g_spmv_dist;
     { static int dbg = -1; if (dbg < 0) { const char *e = getenv("SMLE_SPMV_DEBUG"); dbg = e ? atoi(e) : 0; } args.debug_flags = dbg; }
     kern<<<grid, THREADS + 32, smem, g_stream>>>(args, cg);   // + the producer warp
     ++g_launches;
@@ -876,6 +878,7 @@ struct smle_dist_s {
     int *send_idx = nullptr;
     unsigned int *ticket = nullptr;
     DistCtl ctl;
+    DistCtl *ctl_dev = nullptr;        // device copy (read by the SpMV kernel's epilogue)
     int seq_base = 0;
     cudaGraphExec_t graph = nullptr;
     bool connected = false;
@@ -885,24 +888,34 @@ namespace {
 
 double *dist_p(smle_dist_t d) { return (double *)(d->comm + kDistCtlBytes); }
 
-int dist_launch_iteration(smle_dist_t d, const CgVecArgs &va, const CgScalars &cg)
+int dist_vec_grid(int n)
 {
-    // K1 local SpMV + local p.Ap  ->  post  ->  K2  ->  post  ->  K3  ->  halo push
-    int rc = launch_merge<double, true>(d->a, va.P, va.AP, 1, cg);
-    if (rc) return rc;
-    dist_post_kernel<<<1, 32, 0, g_stream>>>(d->ctl, 0, cg.pAp, cg.ctrl);
-    long long want = ((long long)(va.n >> 1) + kThreads * kVecUnroll - 1) / (kThreads * kVecUnroll);
+    long long want = ((long long)(n >> 1) + kThreads * kVecUnroll - 1) / (kThreads * kVecUnroll);
     int grid = (int)(want < (long long)g_sms * 2 ? want : (long long)g_sms * 2);
-    if (grid < 1) grid = 1;
-    cg1d_update_r_kernel<<<grid, kThreads, 0, g_stream>>>(va, cg, d->ctl);
-    dist_post_kernel<<<1, 32, 0, g_stream>>>(d->ctl, 1, cg.rs_new, cg.ctrl);
-    cg1d_update_xp_kernel<<<grid, kThreads, 0, g_stream>>>(va, cg, d->ctl, 0);
+    return grid < 1 ? 1 : grid;
+}
+
+int dist_push_grid(smle_dist_t d)
+{
     int total = d->ctl.send_off[d->world];
     int pgrid = (total + kThreads - 1) / kThreads;
     if (pgrid < 1) pgrid = 1;
-    if (pgrid > g_sms) pgrid = g_sms;
-    dist_halo_push_kernel<<<pgrid, kThreads, 0, g_stream>>>(d->ctl, va.P, cg.ctrl);
-    g_launches += 5;
+    return pgrid > g_sms ? g_sms : pgrid;
+}
+
+int dist_launch_iteration(smle_dist_t d, const CgVecArgs &va, const CgScalars &cg)
+{
+    // K1 local SpMV + p.Ap posted to the peers | K2 all-reduce -> alpha, r update, r.r posted |
+    // K3 all-reduce -> beta, x/p update, iteration state | halo push + sequence numbers
+    g_spmv_dist = d->ctl_dev;
+    int rc = launch_merge<double, true>(d->a, va.P, va.AP, 1, cg);
+    g_spmv_dist = nullptr;
+    if (rc) return rc;
+    const int grid = dist_vec_grid(va.n);
+    cg1d_update_r_kernel<<<grid, kThreads, 0, g_stream>>>(va, cg, d->ctl);
+    cg1d_update_xp_kernel<<<grid, kThreads, 0, g_stream>>>(va, cg, d->ctl, 0);
+    dist_halo_push_kernel<<<dist_push_grid(d), kThreads, 0, g_stream>>>(d->ctl, va.P, cg.ctrl);
+    g_launches += 3;
     return check_launch("distributed CG iteration");
 }
 
@@ -943,7 +956,7 @@ int smle_dist_create(smle_dist_t *out, smle_csr_t local_a, int rank, int world, 
     c.peer[rank] = c.self;
     c.peer_p[rank] = dist_p(d);
     d->peer_base[rank] = d->comm;
-    d->connected = (world == 1);
+    d->connected = false;   // smle_dist_connect finishes the setup (also for world == 1)
     *out = d;
     return SMLE_OK;
 }
@@ -972,6 +985,8 @@ int smle_dist_connect(smle_dist_t d, const unsigned char *all_handles)
         d->ctl.peer[q] = (DistBlock *)base;
         d->ctl.peer_p[q] = (double *)((unsigned char *)base + kDistCtlBytes);
     }
+    if (!d->ctl_dev) CU(cudaMalloc(&d->ctl_dev, sizeof(DistCtl)));
+    CU(cudaMemcpy(d->ctl_dev, &d->ctl, sizeof(DistCtl), cudaMemcpyHostToDevice));
     d->connected = true;
     return SMLE_OK;
 }
@@ -983,7 +998,7 @@ void smle_dist_destroy(smle_dist_t d)
     if (d->graph) cudaGraphExecDestroy(d->graph);
     for (int q = 0; q < d->world; ++q)
         if (q != d->rank && d->peer_base[q]) cudaIpcCloseMemHandle(d->peer_base[q]);
-    cudaFree(d->comm); cudaFree(d->send_idx); cudaFree(d->ticket);
+    cudaFree(d->comm); cudaFree(d->send_idx); cudaFree(d->ticket); cudaFree(d->ctl_dev);
     delete d;
 }
 
@@ -1034,13 +1049,7 @@ int smle_dist_cg_f64(smle_dist_t d, const double *b_local_dev, double *x_local_d
     if (rc) return rc;
     dist_post_kernel<<<1, 32, 0, g_stream>>>(d->ctl, 2, cg.rs_old, cg.ctrl);
     cg1d_update_xp_kernel<<<1, kThreads, 0, g_stream>>>(va, cg, d->ctl, 1);
-    {
-        int total = d->ctl.send_off[d->world];
-        int pgrid = (total + kThreads - 1) / kThreads;
-        if (pgrid < 1) pgrid = 1;
-        if (pgrid > g_sms) pgrid = g_sms;
-        dist_halo_push_kernel<<<pgrid, kThreads, 0, g_stream>>>(d->ctl, va.P, cg.ctrl);
-    }
+    dist_halo_push_kernel<<<dist_push_grid(d), kThreads, 0, g_stream>>>(d->ctl, va.P, cg.ctrl);
     g_launches += 3;
     rc = check_launch("distributed CG init");
     if (rc) return rc;
@@ -1053,7 +1062,7 @@ int smle_dist_cg_f64(smle_dist_t d, const double *b_local_dev, double *x_local_d
         CU(cudaStreamBeginCapture(g_stream, cudaStreamCaptureModeThreadLocal));
         for (int i = 0; i < kGraphIters && !rc; ++i) rc = dist_launch_iteration(d, va, cg);
         cudaError_t e = cudaStreamEndCapture(g_stream, &graph);
-        g_launches -= 6LL * kGraphIters;
+        g_launches -= 4LL * kGraphIters;
         if (rc) return rc;
         if (e != cudaSuccess) return fail(SMLE_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(e));
         e = cudaGraphInstantiate(&d->graph, graph, 0);
@@ -1067,7 +1076,7 @@ int smle_dist_cg_f64(smle_dist_t d, const double *b_local_dev, double *x_local_d
     auto submit = [&](int slot) -> int {
         if (use_graph) {
             CU(cudaGraphLaunch(d->graph, g_stream));
-            g_launches += 6LL * batch;
+            g_launches += 4LL * batch;
         } else {
             for (int i = 0; i < batch; ++i) {
                 int r2 = dist_launch_iteration(d, va, cg);

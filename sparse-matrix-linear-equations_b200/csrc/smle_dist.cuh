@@ -20,84 +20,15 @@
 #pragma once
 #include "smle_cg.cuh"
 #include "smle_common.cuh"
+#include "smle_distctl.cuh"
 
 namespace smle {
-
-constexpr int kMaxRanks = 8;
-constexpr int kMailKinds = 3;                 // 0: p.Ap   1: r.r   2: b.b (initialisation)
-constexpr size_t kDistCtlBytes = 4096;        // control block in front of the p vector
-
-// layout of the control block (identical on every rank; peers address it through IPC)
-struct DistBlock {
-    unsigned long long halo_seq[kMaxRanks];                           // written by peer q: halo of step seq has landed
-    unsigned long long mail_seq[kMailKinds * 2 * kMaxRanks];
-    double mail_val[kMailKinds * 2 * kMaxRanks];
-    int error;                                                         // spin-wait timeout seen
-};
-static_assert(sizeof(DistBlock) <= kDistCtlBytes, "control block too large");
-
-struct DistCtl {
-    int rank, world;
-    DistBlock *self;                    // local control block
-    DistBlock *peer[kMaxRanks];         // every rank's control block (peer[rank] == self)
-    double *peer_p[kMaxRanks];          // every rank's extended p vector [n_local + n_halo]
-    const int *send_idx;                // local indices of the entries to push, grouped by peer
-    int send_off[kMaxRanks + 1];        // group boundaries
-    int send_dst[kMaxRanks];            // element offset in the peer's p vector where my group lands
-    int needs_from[kMaxRanks];          // 1 when this rank receives halo entries from peer q
-    unsigned int *ticket;
-};
-
-__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p)
-{
-    unsigned long long v;
-    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
-
-__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v)
-{
-    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-
-__device__ __forceinline__ bool dist_spin(const unsigned long long *flag, unsigned long long want, int *error)
-{
-    long long spins = 0;
-    while (ld_acquire_sys(flag) < want) {
-        if (++spins > (1ll << 28)) {   // ~ seconds: a peer died or the launch order is broken
-            *error = 1;
-            return false;
-        }
-    }
-    return true;
-}
-
-// sum of the `kind` mailbox over ranks in rank order (called by one thread)
-__device__ __forceinline__ double dist_wait_sum(const DistCtl &d, int kind, int parity, unsigned long long seq)
-{
-    double s = 0.0;
-    for (int q = 0; q < d.world; ++q) {
-        const int idx = (kind * 2 + parity) * kMaxRanks + q;
-        dist_spin(&d.self->mail_seq[idx], seq, &d.self->error);
-        s += *(volatile double *)&d.self->mail_val[idx];
-    }
-    return s;
-}
 
 // One warp: lane q posts this rank's partial `*value` into peer q's mailbox.
 __global__ void dist_post_kernel(DistCtl d, int kind, const double *value, const int *ctrl)
 {
     if (kind != 2 && ctrl[CTRL_STOP]) return;
-    const int it = ctrl[CTRL_ITER];
-    const unsigned long long seq = (unsigned long long)ctrl[CTRL_SEQ_BASE] + (kind == 2 ? 1ull : (unsigned long long)it + 1ull);
-    const int parity = kind == 2 ? 0 : (it & 1);
-    const int q = threadIdx.x;
-    if (q < d.world) {
-        const int idx = (kind * 2 + parity) * kMaxRanks + d.rank;
-        *(volatile double *)&d.peer[q]->mail_val[idx] = *value;
-        __threadfence_system();
-        st_release_sys(&d.peer[q]->mail_seq[idx], seq);
-    }
+    dist_post(d, kind, *value, ctrl);
 }
 
 // K2 (distributed): alpha from the all-reduced p.Ap, r -= alpha*Ap, local r.r -> cg.rs_new[0]
@@ -159,11 +90,13 @@ cg1d_update_r_kernel(CgVecArgs a, CgScalars cg, DistCtl d)
     }
     if (!last_cta_election(a.ticket, gridDim.x)) return;
     cta_reduce_columns<double>(a.part, nullptr, gridDim.x, 1, cg.rs_new, s_red);   // local r.r
+    dist_post(d, 1, cg.rs_new[0], cg.ctrl);                                        // -> every peer's mailbox
 }
 
 // K3 (distributed).  mode 0: beta / convergence from the all-reduced r.r, x += alpha p,
-// p = r + beta p; the last CTA advances the iteration state.  mode 1 (after cg_init_kernel):
-// only turns the all-reduced b.b into rs_old / bnorm.
+// p = r + beta p (grid-stride: all CTAs sweep one moving window, which keeps the five HBM streams
+// page-friendly -- a per-CTA chunked sweep measured 20 % slower); the last CTA advances the
+// iteration state.  mode 1 (after cg_init_kernel): b.b all-reduce -> rs_old / bnorm.
 __global__ void __launch_bounds__(kThreads)
 cg1d_update_xp_kernel(CgVecArgs a, CgScalars cg, DistCtl d, int mode)
 {
@@ -244,13 +177,13 @@ cg1d_update_xp_kernel(CgVecArgs a, CgScalars cg, DistCtl d, int mode)
     }
 }
 
-// Halo push: P[send_idx] -> the halo tail of each neighbour's p vector, then sequence numbers,
-// then wait for the neighbours' pushes.  When it returns, the next SpMV can start.
+// Halo push: P[send_idx] -> the halo tail of each neighbour's p vector (NVLink peer stores), then
+// sequence numbers, then wait for the neighbours' pushes.  When it retires, the next SpMV can start.
 __global__ void __launch_bounds__(kThreads)
 dist_halo_push_kernel(DistCtl d, const double *__restrict__ P, const int *ctrl)
 {
     if (ctrl[CTRL_STOP]) return;
-    const unsigned long long seq = (unsigned long long)ctrl[CTRL_SEQ_BASE] + (unsigned long long)ctrl[CTRL_ITER] + 1ull;   // step the halo is for
+    const unsigned long long seq = (unsigned long long)ctrl[CTRL_SEQ_BASE] + (unsigned long long)ctrl[CTRL_ITER] + 1ull;
     const int total = d.send_off[d.world];
     for (int i = blockIdx.x * kThreads + threadIdx.x; i < total; i += gridDim.x * kThreads) {
         int q = 0;

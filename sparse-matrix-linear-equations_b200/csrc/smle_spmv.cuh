@@ -21,6 +21,7 @@
 //     y[r]*x[r] (the p.Ap of CG) are accumulated from the same registers.
 #pragma once
 #include "smle_common.cuh"
+#include "smle_distctl.cuh"
 #include "smle_merge.cuh"
 
 namespace smle {
@@ -106,6 +107,7 @@ struct SpmvArgs {
     unsigned int *ticket;
     long long *timing;                 // debug counters (only read with -DSMLE_TIMING)
     int debug_flags;                   // 1: skip compute (stream-only ceiling), 2: skip gathers
+    const DistCtl *dist;               // row-partitioned CG: post the local p.Ap to every peer (else NULL)
 };
 
 template <typename V, int THREADS, int IPT>
@@ -529,7 +531,12 @@ spmv_kernel(SpmvArgs<V> a, CgScalars cg)
     if constexpr (DOT) {
         __syncthreads();
         cta_reduce_columns<V>(a.dot_part, a.fix_part, entries, 1, (V *)cg.pAp, s_red);
-        if (tid == 0) cg.alpha[0] = cg.conv[0] ? 0.0 : cg.rs_old[0] / cg.pAp[0];
+        if (a.dist) {
+            // this rank's partial -> every peer's mailbox; K2 adds the G partials in rank order
+            if constexpr (sizeof(V) == 8) dist_post(*a.dist, 0, (double)cg.pAp[0], cg.ctrl);
+        } else if (tid == 0) {
+            cg.alpha[0] = cg.conv[0] ? 0.0 : cg.rs_old[0] / cg.pAp[0];
+        }
     }
 }
 
