@@ -19,6 +19,7 @@
 #include "smle_cg.cuh"
 #include "smle_merge.cuh"
 #include "smle_spmv.cuh"
+#include "smle_spmm.cuh"
 #include "smle_dist.cuh"
 
 using namespace smle;
@@ -94,6 +95,7 @@ struct Partition {
     int num_tiles = 0;
     int2 *xy = nullptr;   // device, num_tiles + 1
     int *maxlen = nullptr; // device, num_tiles: longest in-tile row segment
+    int max_len = 0;       // max over maxlen[] (host copy): picks the SpMM kernel
 };
 
 struct smle_csr_s {
@@ -107,6 +109,8 @@ struct smle_csr_s {
     void *carry_val = nullptr;  int carry_k = 0;
     void *dot_part = nullptr, *fix_part = nullptr;
     unsigned int *ticket = nullptr;
+    void *tile_carry = nullptr;       // carry slots of spmm_rows_kernel (sentinel-filled)
+    size_t tile_carry_elems = 0;
     CgWorkspace ws;
 };
 
@@ -145,6 +149,16 @@ int get_partition(smle_csr_t a, int items_per_tile, Partition **out)
     ++g_launches;
     rc = check_launch("tile_maxlen_kernel");
     if (rc) return rc;
+    {
+        int *d_max = nullptr;
+        CU(cudaMalloc(&d_max, sizeof(int)));
+        CU(cudaMemsetAsync(d_max, 0, sizeof(int), g_stream));
+        int_max_kernel<<<(p.num_tiles + 255) / 256, 256, 0, g_stream>>>(p.maxlen, p.num_tiles, d_max);
+        ++g_launches;
+        CU(cudaMemcpyAsync(&p.max_len, d_max, sizeof(int), cudaMemcpyDeviceToHost, g_stream));
+        CU(cudaStreamSynchronize(g_stream));
+        cudaFree(d_max);
+    }
     a->parts[items_per_tile] = p;
     *out = &a->parts[items_per_tile];
     return SMLE_OK;
@@ -232,6 +246,160 @@ int launch_merge_t(smle_csr_t a, const V *X, V *Y, int k, const CgScalars &cg, b
     return check_launch("merge_kernel");
 }
 
+
+// k >= 2, no long rows: the TMA-staged row-per-worker kernel (smle_spmm.cuh)
+//   THREADS consumer threads, TILE merge items per tile, STAGES tiles in flight, MINB CTAs per SM.
+// SMLE_SPMM_CFG=<threads>x<tile>x<stages>x<minb> selects one of the instantiated configurations,
+// SMLE_SPMM_CHUNK the number of consecutive tiles per deal (0 = contiguous runs per CTA).
+constexpr int kSpmmRowsMaxLen = 64;    // longest in-tile row segment the row-per-worker kernel accepts
+
+template <typename V>
+int ensure_tile_carry(smle_csr_t a, size_t elems)
+{
+    if (elems <= a->tile_carry_elems) return SMLE_OK;
+    cudaFree(a->tile_carry);
+    a->tile_carry = nullptr; a->tile_carry_elems = 0;
+    CU(cudaMalloc(&a->tile_carry, sizeof(V) * elems));
+    fill_sentinel_kernel<V><<<g_sms * 4, 256, 0, g_stream>>>((V *)a->tile_carry, elems);
+    ++g_launches;
+    a->tile_carry_elems = elems;
+    return check_launch("fill_sentinel_kernel");
+}
+
+int env_int(const char *name, int dflt)
+{
+    const char *e = getenv(name);
+    return e ? atoi(e) : dflt;
+}
+
+template <typename V, int G, int VEC, int NV, int UB, int THREADS, int TILE, int STAGES, int MINB, bool DOT, bool NEAR = false>
+int launch_spmm_rows_t(smle_csr_t a, const V *X, V *Y, int k, const CgScalars &cg, bool dry)
+{
+    using SM = SpmmSmem<V, TILE>;
+    constexpr size_t smem = SM::STAGE_BYTES * STAGES;
+    auto kern = spmm_rows_kernel<V, G, VEC, NV, UB, THREADS, TILE, STAGES, MINB, DOT, NEAR>;
+    Partition *p;
+    int rc = get_partition(a, TILE, &p);
+    if (rc) return rc;
+    rc = ensure_scratch(a, k);
+    if (!rc) rc = ensure_tile_carry<V>(a, (size_t)p->num_tiles * (size_t)k);
+    if (rc) return rc;
+    static int occ = 0;   // per instantiation
+    if (!occ) {
+        CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        // leave the rest of the 256 KB to L1: the dense-row gathers live there
+        int carve = (int)((smem + 2048) * MINB * 100 / (228 * 1024)) + 1;
+        if (carve > 100) carve = 100;
+        CU(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, THREADS + 32, smem));
+        if (occ < 1) return fail(SMLE_ERR_CUDA, "spmm_rows_kernel does not fit on an SM (%zu B smem)", smem);
+        if (occ > MINB) occ = MINB;
+    }
+    if (dry) return SMLE_OK;
+    int grid = g_sms * occ;
+    if (grid > a->max_ctas) grid = a->max_ctas;
+    if (grid > p->num_tiles) grid = p->num_tiles;
+    static int chunk_env = -1;
+    if (chunk_env < 0) chunk_env = env_int("SMLE_SPMM_CHUNK", 1);
+    int chunk = chunk_env > 0 ? chunk_env : (p->num_tiles + grid - 1) / grid;
+    SpmmArgs<V> args;
+    args.ro = a->ro; args.ci = a->ci; args.va = (const V *)a->va;
+    args.X = X; args.Y = Y; args.tile_xy = p->xy;
+    args.m = a->m; args.nnz = a->nnz; args.k = k;
+    args.num_tiles = p->num_tiles; args.chunk = chunk;
+    args.tile_carry = (V *)a->tile_carry;
+    args.dot_part = (V *)a->dot_part;
+    args.ticket = a->ticket;
+    static int ypol = -1;
+    if (ypol < 0) ypol = env_int("SMLE_SPMM_YPOL", 1);
+    args.y_policy = ypol;
+    {
+        // rows of the dense block an L1 budget holds: farther columns cannot be reused from L1
+        static int l1_kb = -1;
+        if (l1_kb < 0) l1_kb = env_int("SMLE_SPMM_L1KB", 96);
+        long long nr = (long long)l1_kb * 1024 / ((long long)k * (long long)sizeof(V));
+        args.near_rows = nr < 1 ? 1 : (nr > (1 << 28) ? (1 << 28) : (int)nr);
+    }
+    kern<<<grid, THREADS + 32, smem, g_stream>>>(args, cg);
+    ++g_launches;
+    return check_launch("spmm_rows_kernel");
+}
+
+// <threads>x<tile>x<stages>x<minb>x<ub>x<nv> as one integer
+constexpr long long spmm_cfg_id(int th, int tl, int st, int mb, int ub, int nv)
+{
+    return ((((long long)th * 10000 + tl) * 10 + st) * 10 + mb) * 1000 + ub * 10 + nv;
+}
+
+long long spmm_cfg()
+{
+    static long long cfg = -1;
+    if (cfg < 0) {
+        cfg = 0;   // 0: the default of the shape
+        const char *e = getenv("SMLE_SPMM_CFG");
+        int th = 0, tl = 0, st = 0, mb = 0, ub = 0, nv = 0;
+        if (e && sscanf(e, "%dx%dx%dx%dx%dx%d", &th, &tl, &st, &mb, &ub, &nv) == 6) cfg = spmm_cfg_id(th, tl, st, mb, ub, nv);
+    }
+    return cfg;
+}
+
+constexpr int kSpmmTile = 2048;
+
+// G, VEC as picked by pick_shape.  Default configuration (sweeps in profiles/): ONE CTA of 30
+// consumer warps + producer per SM (64 registers per thread, so ~4 dense-row loads in flight per
+// warp), tiles of 2048 merge items dealt round-robin (chunk 1).  Blocks wider than 32 lanes
+// (k > 32*VEC) give every lane two vectors so that the fused p.Ap still sees all columns.
+constexpr int kSpmmThreads = 960, kSpmmStages = 2, kSpmmUB = 4;
+
+template <typename V, int G, int VEC, bool DOT>
+int launch_spmm_rows(smle_csr_t a, const V *X, V *Y, int k, const CgScalars &cg, bool dry)
+{
+    const long long cfg = spmm_cfg();
+    if constexpr (G == 16 && VEC == 2 && sizeof(V) == 8) {   // tuning variants (k = 32 fp64 only)
+        if (cfg != 0) {
+#define SMLE_CFG(th, tl, st, mb, ub, nv) \
+    if (cfg == spmm_cfg_id(th, tl, st, mb, ub, nv)) return launch_spmm_rows_t<V, G / nv, VEC, nv, ub, th, tl, st, mb, DOT>(a, X, Y, k, cg, dry);
+#define SMLE_CFGN(th, tl, st, mb, ub, nv) /* L1 no-allocate for far columns: nv + 5 in the id */ \
+    if (cfg == spmm_cfg_id(th, tl, st, mb, ub, nv + 5)) return launch_spmm_rows_t<V, G / nv, VEC, nv, ub, th, tl, st, mb, DOT, true>(a, X, Y, k, cg, dry);
+            SMLE_CFG(480, 1024, 2, 2, 4, 1) SMLE_CFG(224, 512, 2, 4, 4, 1) SMLE_CFG(480, 2048, 2, 2, 4, 1)
+            SMLE_CFG(960, 2048, 2, 1, 4, 1) SMLE_CFG(960, 1024, 2, 1, 4, 1) SMLE_CFG(960, 4096, 2, 1, 4, 1)
+            SMLE_CFG(960, 3072, 2, 1, 4, 1) SMLE_CFG(960, 2048, 3, 1, 4, 1) SMLE_CFG(960, 2048, 2, 1, 3, 1)
+            SMLE_CFG(960, 2048, 2, 1, 8, 1) SMLE_CFG(960, 2048, 2, 1, 4, 2) SMLE_CFG(736, 2048, 2, 1, 6, 1)
+            SMLE_CFGN(960, 2048, 2, 1, 4, 1)
+#undef SMLE_CFG
+#undef SMLE_CFGN
+            return fail(SMLE_ERR_ARG, "unsupported SMLE_SPMM_CFG");
+        }
+    } else if (cfg != 0) {
+        return fail(SMLE_ERR_ARG, "SMLE_SPMM_CFG variants exist for fp64 k = 32 only");
+    }
+    if (G == 32 && k > G * VEC)
+        return launch_spmm_rows_t<V, G, VEC, 2, kSpmmUB, kSpmmThreads, kSpmmTile, kSpmmStages, 1, DOT>(a, X, Y, k, cg, dry);
+    return launch_spmm_rows_t<V, G, VEC, 1, kSpmmUB, kSpmmThreads, kSpmmTile, kSpmmStages, 1, DOT>(a, X, Y, k, cg, dry);
+}
+
+int spmm_tile_items()
+{
+    const long long cfg = spmm_cfg();
+    return cfg ? (int)((cfg / 100000) % 10000) : kSpmmTile;
+}
+
+// does the row-per-worker kernel take this (matrix, k)?   G, VEC: the shape pick_shape chose
+int spmm_use_rows(smle_csr_t a, int G, int VEC, int k, bool dot, bool *use)
+{
+    *use = false;
+    if (getenv("SMLE_SPMM_V1") != nullptr) return SMLE_OK;
+    const int kb = G * VEC * (G == 32 ? 2 : 1);
+    if (dot && k > kb) return SMLE_OK;   // the fused p.Ap needs all k columns in one block
+    static int maxlen = -1;
+    if (maxlen < 0) maxlen = env_int("SMLE_SPMM_ROWS_MAXLEN", kSpmmRowsMaxLen);
+    Partition *p;
+    int rc = get_partition(a, spmm_tile_items(), &p);
+    if (rc) return rc;
+    *use = p->max_len <= maxlen;
+    return SMLE_OK;
+}
+
 // k == 1: the TMA-staged single-vector kernel (smle_spmv.cuh)
 //   THREADS threads per CTA
 //   IPT     merge items per thread per tile (tile = THREADS*IPT items)
@@ -312,8 +480,14 @@ int launch_merge(smle_csr_t a, const V *X, V *Y, int k, const CgScalars &cg, boo
     if (k == 1 && getenv("SMLE_SPMV_V1") == nullptr) return launch_spmv<V, DOT>(a, X, Y, cg, dry);
     int G, VEC;
     pick_shape<V>(k, &G, &VEC);
-#define SMLE_CASE(g, v) \
-    if (G == g && VEC == v) return launch_merge_t<V, g, v, DOT>(a, X, Y, k, cg, dry);
+    bool rows_kernel = false;
+    int rc0 = spmm_use_rows(a, G, VEC, k, DOT, &rows_kernel);
+    if (rc0) return rc0;
+#define SMLE_CASE(g, v)                                                                 \
+    if (G == g && VEC == v) {                                                           \
+        if (rows_kernel) return launch_spmm_rows<V, g, v, DOT>(a, X, Y, k, cg, dry);    \
+        return launch_merge_t<V, g, v, DOT>(a, X, Y, k, cg, dry);                       \
+    }
     if constexpr (sizeof(V) == 8) {
         SMLE_CASE(1, 1) SMLE_CASE(2, 1) SMLE_CASE(4, 1) SMLE_CASE(8, 1) SMLE_CASE(16, 1) SMLE_CASE(32, 1)
         SMLE_CASE(1, 2) SMLE_CASE(2, 2) SMLE_CASE(4, 2) SMLE_CASE(8, 2) SMLE_CASE(16, 2) SMLE_CASE(32, 2)
@@ -751,7 +925,7 @@ void smle_csr_destroy(smle_csr_t a)
     for (auto &kv : a->parts) { cudaFree(kv.second.xy); cudaFree(kv.second.maxlen); }
     cudaFree(a->ro); cudaFree(a->ci); cudaFree(a->va);
     cudaFree(a->carry_row); cudaFree(a->carry_val); cudaFree(a->dot_part); cudaFree(a->fix_part);
-    cudaFree(a->ticket);
+    cudaFree(a->ticket); cudaFree(a->tile_carry);
     delete a;
 }
 
@@ -770,8 +944,17 @@ int smle_csr_tile_coords(smle_csr_t a, int k, int *num_tiles, int *items_per_til
     if (!a || k < 1) return fail(SMLE_ERR_ARG, "bad argument");
     int rc = ensure_init();
     if (rc) return rc;
+    int items = spmv_tile_items();
+    if (k > 1) {   // the tiling of the SpMM kernel that would run for this (matrix, k)
+        int G, VEC;
+        if (a->vbytes == 8) pick_shape<double>(k, &G, &VEC); else pick_shape<float>(k, &G, &VEC);
+        bool rows_kernel = false;
+        rc = spmm_use_rows(a, G, VEC, k, false, &rows_kernel);
+        if (rc) return rc;
+        items = rows_kernel ? spmm_tile_items() : kTileItems;
+    }
     Partition *p;
-    rc = get_partition(a, k == 1 ? spmv_tile_items() : kTileItems, &p);
+    rc = get_partition(a, items, &p);
     if (rc) return rc;
     if (num_tiles) *num_tiles = p->num_tiles;
     if (items_per_tile) *items_per_tile = p->items_per_tile;

@@ -1,0 +1,496 @@
+// smle_spmm.cuh -- TMA-staged tall-skinny SpMM (Y = A X, X n x k row-major), row-per-worker.
+//
+// Replaces OmpMergeCsrmm (reference work_2025/spmm/merge_based.hpp:49-153) for matrices without
+// very long rows (every stencil, most FEM matrices); skewed matrices (wheel, R-MAT hubs) keep the
+// merge-walk kernel of smle_merge.cuh.  The decomposition is still the reference's merge path:
+// tiles are equal shares of (row ends + nonzeros), a tile owns the rows that END inside it plus
+// the leading part of the row it stops in, whose partial sum is a carry-out.
+//
+// B200 mapping:
+//   * persistent CTAs (all co-resident), a producer warp streaming column indices / values / row
+//     offsets of each tile through shared memory with cp.async.bulk + mbarriers (L2 evict-first:
+//     A is read once per product), consumer warps that never meet at a CTA-wide barrier;
+//   * tiles are dealt to CTAs ROUND-ROBIN in chunks of `chunk` consecutive tiles, so at any
+//     moment the whole GPU works on one compact window of rows.  The dense block does not fit in
+//     L2 (2 GB at 200^3 x 32), but the window plus the off-diagonal planes it touches does, so
+//     every dense row comes from DRAM once instead of once per stencil plane;
+//   * a WORKER of G lanes owns one row at a time and covers G*VEC = min(k, 32*VEC) columns with
+//     VEC-wide (128-bit) loads of the dense rows: every nonzero (broadcast from shared memory) is
+//     reused across all k right-hand sides, and all dense-row loads of a row chunk are issued
+//     before the first FMA.  Workers sit on W consecutive rows, so the near-diagonal gathers hit
+//     L1;
+//   * carries without fix-up passes and without waiting: the two tiles that share a cut row meet
+//     in a global slot (one per tile and column).  Each swaps its part in with an atomic
+//     exchange; the slot holds a signalling-NaN bit pattern that no arithmetic result can have
+//     while it is empty, so the party that finds a value there knows it came second, stores the
+//     finished row element (owner part + carry, the reference's order, merge_based.hpp:146 --
+//     the same sum whoever finishes) and re-arms the slot.  No fences (they would invalidate
+//     L1), no per-launch reset, no dependence on how tiles are scheduled;
+//   * DOT adds the per-column p.Ap of CG while rows are stored; the last CTA reduces the per-CTA
+//     partials in CTA order (deterministic) and forms alpha.
+#pragma once
+#include "smle_spmv.cuh"
+
+namespace smle {
+
+template <typename V> struct CarrySentinel;
+template <> struct CarrySentinel<double> { static constexpr unsigned long long bits = 0xFFF75EA1C0DED00Dull; };
+template <> struct CarrySentinel<float> { static constexpr unsigned int bits = 0xFFA5C0DEu; };
+
+template <typename V>
+__device__ __forceinline__ bool is_sentinel(V v)
+{
+    if constexpr (sizeof(V) == 8) return (unsigned long long)__double_as_longlong(v) == CarrySentinel<double>::bits;
+    else return __float_as_uint(v) == CarrySentinel<float>::bits;
+}
+
+template <typename V>
+__device__ __forceinline__ V sentinel_value()
+{
+    if constexpr (sizeof(V) == 8) return __longlong_as_double((long long)CarrySentinel<double>::bits);
+    else return __uint_as_float(CarrySentinel<float>::bits);
+}
+
+template <typename V>
+__global__ void fill_sentinel_kernel(V *p, size_t count)
+{
+    const V s = sentinel_value<V>();
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (size_t)gridDim.x * blockDim.x)
+        p[i] = s;
+}
+
+// L2-coherent (volatile) vector access to a carry slot: VEC*sizeof(V) in {4, 8, 16} bytes
+template <typename V, int VEC>
+__device__ __forceinline__ void ld_volatile_vec(V (&out)[VEC], const V *p)
+{
+    if constexpr (sizeof(V) * VEC == 16) {
+        uint4 t;
+        asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];"
+                     : "=r"(t.x), "=r"(t.y), "=r"(t.z), "=r"(t.w) : "l"(p) : "memory");
+        memcpy(out, &t, 16);
+    } else if constexpr (sizeof(V) * VEC == 8) {
+        uint2 t;
+        asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(t.x), "=r"(t.y) : "l"(p) : "memory");
+        memcpy(out, &t, 8);
+    } else {
+        unsigned int t;
+        asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(t) : "l"(p) : "memory");
+        memcpy(out, &t, 4);
+    }
+}
+
+template <typename V, int VEC>
+__device__ __forceinline__ void st_volatile_vec(V *p, const V (&in)[VEC])
+{
+    if constexpr (sizeof(V) * VEC == 16) {
+        uint4 t;
+        memcpy(&t, in, 16);
+        asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(t.x), "r"(t.y), "r"(t.z), "r"(t.w)
+                     : "memory");
+    } else if constexpr (sizeof(V) * VEC == 8) {
+        uint2 t;
+        memcpy(&t, in, 8);
+        asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(t.x), "r"(t.y) : "memory");
+    } else {
+        unsigned int t;
+        memcpy(&t, in, 4);
+        asm volatile("st.volatile.global.u32 [%0], %1;" ::"l"(p), "r"(t) : "memory");
+    }
+}
+
+// streaming store of an output row (read next by a different kernel, never by this one)
+template <typename V, int VEC>
+__device__ __forceinline__ void st_stream_vec(V *p, const V (&in)[VEC], uint64_t pol)
+{
+    if constexpr (sizeof(V) * VEC == 16) {
+        uint4 t;
+        memcpy(&t, in, 16);
+        asm volatile("st.global.L2::cache_hint.v4.u32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(p), "r"(t.x), "r"(t.y), "r"(t.z),
+                     "r"(t.w), "l"(pol)
+                     : "memory");
+    } else if constexpr (sizeof(V) * VEC == 8) {
+        uint2 t;
+        memcpy(&t, in, 8);
+        asm volatile("st.global.L2::cache_hint.v2.u32 [%0], {%1, %2}, %3;" ::"l"(p), "r"(t.x), "r"(t.y), "l"(pol) : "memory");
+    } else {
+        unsigned int t;
+        memcpy(&t, in, 4);
+        asm volatile("st.global.L2::cache_hint.u32 [%0], %1, %2;" ::"l"(p), "r"(t), "l"(pol) : "memory");
+    }
+}
+
+// stage layout: like SpmvSmem, with room behind the column indices for the over-read of one pass
+template <typename V, int TILE>
+struct SpmmSmem {
+    static constexpr int EPV = 16 / (int)sizeof(V);
+    static constexpr int COL_WORDS = TILE + 32;
+    static constexpr int VAL_ELEMS = TILE + 2 * EPV;
+    static constexpr int RO_WORDS = TILE + 8;
+    static constexpr size_t STAGE_BYTES =
+        ((size_t)COL_WORDS * 4 + (size_t)VAL_ELEMS * sizeof(V) + (size_t)RO_WORDS * 4 + 15) / 16 * 16;
+};
+
+// dense-row load that does not allocate in L1 (for columns too far from the diagonal to be reused
+// before the lines in between have pushed them out)
+template <typename V, int VEC>
+__device__ __forceinline__ void ldg_vec_na(V (&out)[VEC], const V *p)
+{
+    if constexpr (sizeof(V) * VEC == 16) {
+        uint4 t;
+        asm("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(t.x), "=r"(t.y), "=r"(t.z), "=r"(t.w) : "l"(p));
+        memcpy(out, &t, 16);
+    } else if constexpr (sizeof(V) * VEC == 8) {
+        uint2 t;
+        asm("ld.global.nc.L1::no_allocate.v2.u32 {%0, %1}, [%2];" : "=r"(t.x), "=r"(t.y) : "l"(p));
+        memcpy(out, &t, 8);
+    } else {
+        unsigned int t;
+        asm("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(t) : "l"(p));
+        memcpy(out, &t, 4);
+    }
+}
+
+template <typename V>
+struct SpmmArgs {
+    const int *__restrict__ ro;
+    const int *__restrict__ ci;
+    const V *__restrict__ va;
+    const V *__restrict__ X;
+    V *__restrict__ Y;
+    const int2 *__restrict__ tile_xy;
+    int m, nnz, k;
+    int num_tiles;
+    int chunk;                         // consecutive tiles a CTA takes before the deal moves on
+    V *tile_carry;                     // [num_tiles * k] carry slots, sentinel when empty
+    V *dot_part;                       // [gridDim.x * k]  (DOT)
+    unsigned int *ticket;
+    int y_policy;                      // 1: stream Y with L2 evict-first
+    int near_rows;                     // |column - row| beyond this: the dense row is not kept in L1 (0: keep all)
+};
+
+
+// ---- wait-free carry exchange ------------------------------------------------------------------
+// Slot t holds the sentinel until one of the two parties of the row cut by the boundary between
+// tiles t and t+1 arrives: the tile that has the row's leading part (publisher) or the tile the
+// row continues in (owner).  Each swaps its value in; whoever finds the other's value there
+// finishes the row (owner part + carry, the reference's order) and re-arms the slot.  Nobody
+// ever waits, so the schedule of tiles over CTAs is free.
+template <typename V>
+__device__ __forceinline__ V slot_exchange(V *slot, V mine)
+{
+    if constexpr (sizeof(V) == 8) {
+        const unsigned long long o = atomicExch(reinterpret_cast<unsigned long long *>(slot),
+                                                (unsigned long long)__double_as_longlong(mine));
+        return __longlong_as_double((long long)o);
+    } else {
+        const unsigned int o = atomicExch(reinterpret_cast<unsigned int *>(slot), __float_as_uint(mine));
+        return __uint_as_float(o);
+    }
+}
+
+template <typename V>
+__device__ __forceinline__ void slot_reset(V *slot)
+{
+    *reinterpret_cast<volatile V *>(slot) = sentinel_value<V>();
+}
+
+// val = sum of the parts of row tile_xy[tt+1].x that lie in tiles <= tt, column c.
+// Returns the row element's share of the dot product X[row,c]*Y[row,c] when it finished the row.
+template <typename V, bool DOT>
+__device__ __noinline__ V carry_publish(const int2 *__restrict__ tile_xy, V *tile_carry, V *Y, const V *X, int m, int k,
+                                        int tt, int c, V val)
+{
+    for (;;) {
+        const int row = tile_xy[tt + 1].x;
+        if (row >= m) return V(0);
+        V *slot = tile_carry + (size_t)tt * (size_t)k + c;
+        const V owner = slot_exchange<V>(slot, val);
+        if (is_sentinel<V>(owner)) return V(0);            // the owner tile comes later and finishes
+        slot_reset<V>(slot);
+        if (tile_xy[tt + 2].x > row) {                     // the row ends in tile tt+1
+            const size_t off = (size_t)row * (size_t)k + c;
+            const V fin = owner + val;
+            Y[off] = fin;
+            if constexpr (DOT) return fin * __ldg(X + off);
+            return V(0);
+        }
+        val = val + owner;                                 // tile tt+1 lies inside the row: pass on
+        ++tt;
+    }
+}
+
+// Template parameters
+//   G, VEC, NV  a worker is G lanes; a lane holds NV vectors of VEC consecutive columns (VEC*sizeof(V)
+//               <= 16 B), vector q at column cb*KB + q*G*VEC + li*VEC, so every load instruction of a
+//               worker covers G*VEC*sizeof(V) contiguous bytes and a worker covers KB = G*VEC*NV columns
+//   UB          nonzeros of a row whose dense rows are requested before the first FMA
+//   THREADS     consumer threads (+ one producer warp);  TILE merge items per tile;  STAGES tiles
+//               in flight;  MINB CTAs per SM
+//   DOT         also accumulate X[r,:].Y[r,:] (p.Ap of CG); needs k <= KB (one column block)
+//   NEAR        dense rows of columns farther than near_rows from the diagonal bypass L1 allocation
+template <typename V, int G, int VEC, int NV, int UB, int THREADS, int TILE, int STAGES, int MINB, bool DOT, bool NEAR>
+__global__ void __launch_bounds__(THREADS + 32, MINB)
+spmm_rows_kernel(SpmmArgs<V> a, CgScalars cg)
+{
+    using SM = SpmmSmem<V, TILE>;
+    static_assert(UB <= 16, "over-read room behind the staged column indices");
+    constexpr int NW = THREADS / 32;
+    constexpr int EPV = SM::EPV;
+    constexpr int W = THREADS / G;         // workers per CTA
+    constexpr int HB = G * VEC;            // columns per load instruction of a worker
+    constexpr int KB = HB * NV;            // columns per column block
+
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ uint64_t s_full[STAGES], s_empty[STAGES];
+    __shared__ V s_wsum[DOT ? NW : 1][DOT ? KB : 1];
+    __shared__ V s_red[THREADS + 32];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int w = tid / G, li = tid % G;
+    const size_t k = (size_t)a.k;
+
+    if constexpr (DOT) {
+        if (cg.ctrl[CTRL_STOP]) {
+            if (blockIdx.x == 0 && tid == 0) cg.ctrl[CTRL_HALT] = 1;
+            return;
+        }
+    }
+
+    // tile schedule: iteration `it` of CTA b -> tile ((it / chunk) * grid + b) * chunk + it % chunk
+    const int chunk = a.chunk;
+    const int stride = (int)gridDim.x * chunk;
+    auto tile_of = [&](int it) { return (it / chunk) * stride + (int)blockIdx.x * chunk + it % chunk; };
+
+    auto stage_col = [&](int s) { return reinterpret_cast<int *>(smem_raw + (size_t)s * SM::STAGE_BYTES); };
+    auto stage_val = [&](int s) {
+        return reinterpret_cast<V *>(smem_raw + (size_t)s * SM::STAGE_BYTES + (size_t)SM::COL_WORDS * 4);
+    };
+    auto stage_ro = [&](int s) {
+        return reinterpret_cast<int *>(smem_raw + (size_t)s * SM::STAGE_BYTES + (size_t)SM::COL_WORDS * 4 +
+                                       (size_t)SM::VAL_ELEMS * sizeof(V));
+    };
+
+    if (tid == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&s_full[s], 1); mbar_init(&s_empty[s], NW); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    // The gathers of a pass read UB column indices without looking at the row end; what lies behind
+    // a tile's staged indices must therefore always be a valid column: zero now, indices of earlier
+    // tiles later.
+    for (int s = 0; s < STAGES; ++s)
+        for (int i = tid; i < SM::COL_WORDS; i += blockDim.x) stage_col(s)[i] = 0;
+    fence_proxy_async();
+    __syncthreads();
+
+    V dot[NV][VEC];
+#pragma unroll
+    for (int q = 0; q < NV; ++q)
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) dot[q][v] = 0;
+
+    if (warp == NW) {
+        // =============================== producer warp ===========================================
+        if (lane == 0) {
+            const uint64_t pol_stream = l2_policy_evict_first();
+            for (int it = 0;; ++it) {
+                const int t = tile_of(it);
+                if (t >= a.num_tiles) break;
+                const int s = it % STAGES;
+                const int2 lo = a.tile_xy[t], hi = a.tile_xy[t + 1];
+                if (it >= STAGES) {
+                    mbar_wait(&s_empty[s], (uint32_t)(it / STAGES - 1) & 1u);
+                    fence_proxy_async();
+                }
+                const int yc = lo.y & ~3, yv = lo.y & ~(EPV - 1), rb = (lo.x + 1) & ~3;
+                const uint32_t nb_col = (uint32_t)((hi.y - yc + 3) & ~3) * 4u;
+                const uint32_t nb_val = (uint32_t)((hi.y - yv + EPV - 1) & ~(EPV - 1)) * (uint32_t)sizeof(V);
+                const uint32_t nb_ro = (uint32_t)((hi.x + 2 - rb + 3) & ~3) * 4u;
+                mbar_expect_tx(&s_full[s], nb_col + nb_val + nb_ro);
+                if (nb_col) tma_load_1d(stage_col(s), a.ci + yc, nb_col, &s_full[s], pol_stream);
+                if (nb_val) tma_load_1d(stage_val(s), a.va + yv, nb_val, &s_full[s], pol_stream);
+                tma_load_1d(stage_ro(s), a.ro + rb, nb_ro, &s_full[s], pol_stream);
+            }
+        }
+    } else {
+        // =============================== consumer warps ==========================================
+        const uint64_t pol_y = l2_policy_evict_first();
+        const int num_cb = DOT ? 1 : (a.k + KB - 1) / KB;
+        const unsigned kbytes = (unsigned)a.k * (unsigned)sizeof(V);   // bytes per dense row
+        const unsigned near2 = 2u * (unsigned)a.near_rows;
+        int2 nxt_lo = make_int2(0, 0), nxt_hi = make_int2(0, 0);
+        {
+            const int t = tile_of(0);
+            if (t < a.num_tiles) { nxt_lo = a.tile_xy[t]; nxt_hi = a.tile_xy[t + 1]; }
+        }
+        for (int it = 0;; ++it) {
+            const int t = tile_of(it);
+            if (t >= a.num_tiles) break;
+            const int s = it % STAGES;
+            const uint32_t parity = (uint32_t)(it / STAGES) & 1u;
+            const int2 lo = nxt_lo, hi = nxt_hi;
+            {
+                const int tn = tile_of(it + 1);
+                if (tn < a.num_tiles) { nxt_lo = a.tile_xy[tn]; nxt_hi = a.tile_xy[tn + 1]; }
+            }
+            const int x0 = lo.x, y0 = lo.y;
+            const int rows = hi.x - x0, nz = hi.y - y0;
+            const int yc = y0 & ~3, yv = y0 & ~(EPV - 1), rb = (x0 + 1) & ~3;
+            const int *s_re = stage_ro(s) + (x0 + 1 - rb);   // s_re[i] = end offset of local row i
+            const int *pc = stage_col(s) + (y0 - yc);
+            const V *pv = stage_val(s) + (y0 - yv);
+            // Carries: pseudo-row `rows` is the part of row hi.x that lies in this tile (it continues
+            // in tile t+1); local row 0 may have begun in tile t-1.  Both sides meet in slot t-1 / t.
+            const bool has_in = t > 0 && x0 < a.m;
+
+            mbar_wait(&s_full[s], parity);
+
+            for (int cb = 0; cb < num_cb; ++cb) {
+                // columns of this lane; lanes past k read column block 0 instead and store nothing
+                int coff[NV];
+                bool ok[NV];
+                const char *xlane[NV];
+#pragma unroll
+                for (int q = 0; q < NV; ++q) {
+                    coff[q] = cb * KB + q * HB + li * VEC;
+                    ok[q] = coff[q] < a.k;
+                    if (!ok[q]) coff[q] = 0;
+                    xlane[q] = reinterpret_cast<const char *>(a.X + coff[q]);
+                }
+                for (int i = w; i <= rows; i += W) {
+                    const int beg0 = (i == 0) ? 0 : s_re[i - 1] - y0;
+                    const int end = (i == rows) ? nz : s_re[i] - y0;
+                    const bool is_out = (i == rows), is_in = (i == 0) && has_in;
+                    if (is_out && hi.x >= a.m) continue;   // behind the last row: nothing to produce
+                    const int grow = x0 + i;
+                    V acc[NV][VEC];
+#pragma unroll
+                    for (int q = 0; q < NV; ++q)
+#pragma unroll
+                        for (int v = 0; v < VEC; ++v) acc[q][v] = 0;
+                    V xr[NV][VEC];
+                    if constexpr (DOT) {
+                        if (!is_out) {
+#pragma unroll
+                            for (int q = 0; q < NV; ++q)
+                                ldg_vec<V, VEC>(xr[q], reinterpret_cast<const V *>(xlane[q] + (size_t)(unsigned)(x0 + i) * kbytes));
+                        }
+                    }
+                    for (int beg = beg0; beg < end; beg += UB) {
+                        // UB dense rows requested per pass; ptxas keeps about as many loads in flight per
+                        // warp as it has scoreboards, the rest of the latency is hidden by the other warps
+                        const int *pcb = pc + beg;
+                        const V *pvb = pv + beg;
+                        const int cnt = end - beg;
+                        V xv[UB][NV][VEC];
+#pragma unroll
+                        for (int u = 0; u < UB; ++u) {      // unconditional: slots behind the row read valid columns
+                            const int col = pcb[u];
+                            const size_t xrow = (size_t)(unsigned)col * kbytes;
+                            if constexpr (NEAR) {
+                                const bool far = (unsigned)(col - grow + a.near_rows) > near2;
+#pragma unroll
+                                for (int q = 0; q < NV; ++q) {
+                                    const V *src = reinterpret_cast<const V *>(xlane[q] + xrow);
+                                    if (far) ldg_vec_na<V, VEC>(xv[u][q], src);
+                                    else ldg_vec<V, VEC>(xv[u][q], src);
+                                }
+                            } else {
+#pragma unroll
+                                for (int q = 0; q < NV; ++q)
+                                    ldg_vec<V, VEC>(xv[u][q], reinterpret_cast<const V *>(xlane[q] + xrow));
+                            }
+                        }
+#pragma unroll
+                        for (int u = 0; u < UB; ++u)
+                            if (u < cnt) {
+                                const V av = pvb[u];
+#pragma unroll
+                                for (int q = 0; q < NV; ++q)
+#pragma unroll
+                                    for (int v = 0; v < VEC; ++v) acc[q][v] += av * xv[u][q][v];
+                            }
+                    }
+                    if (is_in || is_out) {
+#pragma unroll
+                        for (int q = 0; q < NV; ++q) {
+                            if (!ok[q]) continue;
+#pragma unroll
+                            for (int v = 0; v < VEC; ++v) {
+                                const int c = coff[q] + v;
+                                V d = 0;
+                                if (is_in) {
+                                    // this row began in tile t-1: meet its carry in slot t-1
+                                    V *slot = a.tile_carry + (size_t)(t - 1) * k + c;
+                                    const V other = slot_exchange<V>(slot, acc[q][v]);
+                                    if (!is_sentinel<V>(other)) {      // the carry was there first: finish here
+                                        slot_reset<V>(slot);
+                                        if (!is_out) {
+                                            const V fin = acc[q][v] + other;
+                                            a.Y[(size_t)(x0 + i) * k + c] = fin;
+                                            if constexpr (DOT) d = fin * xr[q][v];
+                                        } else {                       // no row ends in this tile: pass on
+                                            d = carry_publish<V, DOT>(a.tile_xy, a.tile_carry, a.Y, a.X, a.m, a.k, t, c,
+                                                                      other + acc[q][v]);
+                                        }
+                                    }
+                                } else {
+                                    d = carry_publish<V, DOT>(a.tile_xy, a.tile_carry, a.Y, a.X, a.m, a.k, t, c, acc[q][v]);
+                                }
+                                if constexpr (DOT) dot[q][v] += d;
+                            }
+                        }
+                    } else {
+#pragma unroll
+                        for (int q = 0; q < NV; ++q) {
+                            if (!ok[q]) continue;
+                            V *dst = a.Y + (size_t)(x0 + i) * k + coff[q];
+                            if (a.y_policy) st_stream_vec<V, VEC>(dst, acc[q], pol_y);
+                            else st_vec<V, VEC>(dst, acc[q]);
+                            if constexpr (DOT) {
+#pragma unroll
+                                for (int v = 0; v < VEC; ++v) dot[q][v] += acc[q][v] * xr[q][v];
+                            }
+                        }
+                    }
+                }
+            }
+
+            // release the stage: one arrival per consumer warp
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&s_empty[s]);
+        }
+    }
+
+    if constexpr (!DOT) return;
+
+    // ---- per-CTA dot partials, last CTA: pAp and alpha (no_pretreatment.hpp:107-120) --------------
+    if constexpr (DOT) {
+#pragma unroll
+        for (int d = G; d < 32; d <<= 1) {
+#pragma unroll
+            for (int q = 0; q < NV; ++q)
+#pragma unroll
+                for (int v = 0; v < VEC; ++v) dot[q][v] += __shfl_xor_sync(0xffffffffu, dot[q][v], d);
+        }
+        __syncthreads();
+        if (warp < NW && lane / G == 0) {
+#pragma unroll
+            for (int q = 0; q < NV; ++q)
+#pragma unroll
+                for (int v = 0; v < VEC; ++v) s_wsum[warp][q * HB + li * VEC + v] = dot[q][v];
+        }
+        __syncthreads();
+        if (tid < KB && tid < a.k) {
+            V sdot = 0;
+            for (int wi = 0; wi < NW; ++wi) sdot += s_wsum[wi][tid];
+            a.dot_part[(size_t)blockIdx.x * k + tid] = sdot;
+        }
+        if (!last_cta_election(a.ticket, gridDim.x)) return;
+        cta_reduce_columns<V>(a.dot_part, nullptr, gridDim.x, a.k, (V *)cg.pAp, s_red);
+        for (int c = tid; c < a.k; c += blockDim.x)
+            cg.alpha[c] = cg.conv[c] ? 0.0 : cg.rs_old[c] / cg.pAp[c];
+    }
+}
+
+} // namespace smle

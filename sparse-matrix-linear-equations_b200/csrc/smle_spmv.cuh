@@ -146,6 +146,14 @@ __global__ void tile_maxlen_kernel(const int *__restrict__ ro, const int2 *__res
     if (lane == 0) out[t] = mx;
 }
 
+__global__ void int_max_kernel(const int *__restrict__ v, int n, int *out)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    int mx = i < n ? v[i] : 0;
+    mx = __reduce_max_sync(0xffffffffu, mx);
+    if ((threadIdx.x & 31) == 0 && mx > 0) atomicMax(out, mx);
+}
+
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar)
 {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -181,16 +189,17 @@ __device__ __forceinline__ V row_sum(const V *__restrict__ x, const int *pc, con
 {
     constexpr int UB = 8;
     V sum = 0;
-    do {
+    while (beg < end) {
+        // unconditional gathers (slots behind the row repeat its last nonzero: same address, an L1
+        // hit): no predicate keeps ptxas from issuing all UB requests before the first FMA
         V xa[UB];
 #pragma unroll
-        for (int j = 0; j < UB; ++j)
-            if (beg + j < end) xa[j] = __ldg(x + pc[beg + j]);
+        for (int j = 0; j < UB; ++j) xa[j] = __ldg(x + pc[min(beg + j, end - 1)]);
 #pragma unroll
         for (int j = 0; j < UB; ++j)
             if (beg + j < end) sum += pv[beg + j] * xa[j];
         beg += UB;
-    } while (beg < end);
+    }
     return sum;
 }
 
