@@ -272,12 +272,12 @@ int env_int(const char *name, int dflt)
     return e ? atoi(e) : dflt;
 }
 
-template <typename V, int G, int VEC, int NV, int UB, int THREADS, int TILE, int STAGES, int MINB, bool DOT, bool NEAR = false>
+template <typename V, int G, int VEC, int NV, int UB, int THREADS, int TILE, int STAGES, int MINB, bool DOT>
 int launch_spmm_rows_t(smle_csr_t a, const V *X, V *Y, int k, const CgScalars &cg, bool dry)
 {
     using SM = SpmmSmem<V, TILE>;
     constexpr size_t smem = SM::STAGE_BYTES * STAGES;
-    auto kern = spmm_rows_kernel<V, G, VEC, NV, UB, THREADS, TILE, STAGES, MINB, DOT, NEAR>;
+    auto kern = spmm_rows_kernel<V, G, VEC, NV, UB, THREADS, TILE, STAGES, MINB, DOT>;
     Partition *p;
     int rc = get_partition(a, TILE, &p);
     if (rc) return rc;
@@ -288,8 +288,13 @@ int launch_spmm_rows_t(smle_csr_t a, const V *X, V *Y, int k, const CgScalars &c
     if (!occ) {
         CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         // leave the rest of the 256 KB to L1: the dense-row gathers live there
-        int carve = (int)((smem + 2048) * MINB * 100 / (228 * 1024)) + 1;
-        if (carve > 100) carve = 100;
+        // (the carve-out comes in steps; every CTA also takes 1 KB of reserved shared memory)
+        cudaFuncAttributes fa;
+        CU(cudaFuncGetAttributes(&fa, kern));
+        const size_t need = (smem + fa.sharedSizeBytes + 1024) * MINB;
+        int carve = 100;
+        for (int kb : {8, 16, 32, 64, 100, 132, 164, 196, 228})
+            if (need <= (size_t)kb * 1024) { carve = (kb * 100 + 227) / 228; break; }
         CU(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
         CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, THREADS + 32, smem));
         if (occ < 1) return fail(SMLE_ERR_CUDA, "spmm_rows_kernel does not fit on an SM (%zu B smem)", smem);
@@ -300,7 +305,7 @@ int launch_spmm_rows_t(smle_csr_t a, const V *X, V *Y, int k, const CgScalars &c
     if (grid > a->max_ctas) grid = a->max_ctas;
     if (grid > p->num_tiles) grid = p->num_tiles;
     static int chunk_env = -1;
-    if (chunk_env < 0) chunk_env = env_int("SMLE_SPMM_CHUNK", 1);
+    if (chunk_env < 0) chunk_env = env_int("SMLE_SPMM_CHUNK", 2);
     int chunk = chunk_env > 0 ? chunk_env : (p->num_tiles + grid - 1) / grid;
     SpmmArgs<V> args;
     args.ro = a->ro; args.ci = a->ci; args.va = (const V *)a->va;
@@ -313,13 +318,6 @@ int launch_spmm_rows_t(smle_csr_t a, const V *X, V *Y, int k, const CgScalars &c
     static int ypol = -1;
     if (ypol < 0) ypol = env_int("SMLE_SPMM_YPOL", 1);
     args.y_policy = ypol;
-    {
-        // rows of the dense block an L1 budget holds: farther columns cannot be reused from L1
-        static int l1_kb = -1;
-        if (l1_kb < 0) l1_kb = env_int("SMLE_SPMM_L1KB", 96);
-        long long nr = (long long)l1_kb * 1024 / ((long long)k * (long long)sizeof(V));
-        args.near_rows = nr < 1 ? 1 : (nr > (1 << 28) ? (1 << 28) : (int)nr);
-    }
     kern<<<grid, THREADS + 32, smem, g_stream>>>(args, cg);
     ++g_launches;
     return check_launch("spmm_rows_kernel");
@@ -343,11 +341,13 @@ long long spmm_cfg()
     return cfg;
 }
 
-constexpr int kSpmmTile = 2048;
+constexpr int kSpmmTile = 1920;
 
-// G, VEC as picked by pick_shape.  Default configuration (sweeps in profiles/): ONE CTA of 30
-// consumer warps + producer per SM (64 registers per thread, so ~4 dense-row loads in flight per
-// warp), tiles of 2048 merge items dealt round-robin (chunk 1).  Blocks wider than 32 lanes
+// G, VEC as picked by pick_shape.  Default configuration (sweeps in profiles/r01_spmm_sweeps.txt):
+// ONE CTA of 30 consumer warps + producer per SM (64 registers per thread; ptxas keeps ~4 dense-row
+// loads in flight per warp, the scoreboard count), tiles of 1920 merge items (~4 rows per worker
+// for a 7-point stencil, 2 stages = 62 KB so the carve-out stays at 64 KB and L1 at 192 KB), dealt
+// round-robin in chunks of 2.  Blocks wider than 32 lanes
 // (k > 32*VEC) give every lane two vectors so that the fused p.Ap still sees all columns.
 constexpr int kSpmmThreads = 960, kSpmmStages = 2, kSpmmUB = 4;
 
@@ -359,15 +359,12 @@ int launch_spmm_rows(smle_csr_t a, const V *X, V *Y, int k, const CgScalars &cg,
         if (cfg != 0) {
 #define SMLE_CFG(th, tl, st, mb, ub, nv) \
     if (cfg == spmm_cfg_id(th, tl, st, mb, ub, nv)) return launch_spmm_rows_t<V, G / nv, VEC, nv, ub, th, tl, st, mb, DOT>(a, X, Y, k, cg, dry);
-#define SMLE_CFGN(th, tl, st, mb, ub, nv) /* L1 no-allocate for far columns: nv + 5 in the id */ \
-    if (cfg == spmm_cfg_id(th, tl, st, mb, ub, nv + 5)) return launch_spmm_rows_t<V, G / nv, VEC, nv, ub, th, tl, st, mb, DOT, true>(a, X, Y, k, cg, dry);
             SMLE_CFG(480, 1024, 2, 2, 4, 1) SMLE_CFG(224, 512, 2, 4, 4, 1) SMLE_CFG(480, 2048, 2, 2, 4, 1)
             SMLE_CFG(960, 2048, 2, 1, 4, 1) SMLE_CFG(960, 1024, 2, 1, 4, 1) SMLE_CFG(960, 4096, 2, 1, 4, 1)
             SMLE_CFG(960, 3072, 2, 1, 4, 1) SMLE_CFG(960, 2048, 3, 1, 4, 1) SMLE_CFG(960, 2048, 2, 1, 3, 1)
-            SMLE_CFG(960, 2048, 2, 1, 8, 1) SMLE_CFG(960, 2048, 2, 1, 4, 2) SMLE_CFG(736, 2048, 2, 1, 6, 1)
-            SMLE_CFGN(960, 2048, 2, 1, 4, 1)
+            SMLE_CFG(960, 2000, 2, 1, 4, 1) SMLE_CFG(960, 1920, 2, 1, 4, 1) SMLE_CFG(960, 1440, 2, 1, 4, 1)
+            SMLE_CFG(960, 1536, 2, 1, 4, 1) SMLE_CFG(960, 1920, 2, 1, 8, 1) SMLE_CFG(960, 2000, 2, 1, 8, 1) SMLE_CFG(960, 1920, 2, 1, 6, 1)
 #undef SMLE_CFG
-#undef SMLE_CFGN
             return fail(SMLE_ERR_ARG, "unsupported SMLE_SPMM_CFG");
         }
     } else if (cfg != 0) {

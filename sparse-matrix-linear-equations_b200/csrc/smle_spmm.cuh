@@ -123,32 +123,14 @@ __device__ __forceinline__ void st_stream_vec(V *p, const V (&in)[VEC], uint64_t
 template <typename V, int TILE>
 struct SpmmSmem {
     static constexpr int EPV = 16 / (int)sizeof(V);
-    static constexpr int COL_WORDS = TILE + 32;
+    static constexpr int COL_WORDS = TILE + 24;
     static constexpr int VAL_ELEMS = TILE + 2 * EPV;
     static constexpr int RO_WORDS = TILE + 8;
     static constexpr size_t STAGE_BYTES =
         ((size_t)COL_WORDS * 4 + (size_t)VAL_ELEMS * sizeof(V) + (size_t)RO_WORDS * 4 + 15) / 16 * 16;
 };
 
-// dense-row load that does not allocate in L1 (for columns too far from the diagonal to be reused
-// before the lines in between have pushed them out)
-template <typename V, int VEC>
-__device__ __forceinline__ void ldg_vec_na(V (&out)[VEC], const V *p)
-{
-    if constexpr (sizeof(V) * VEC == 16) {
-        uint4 t;
-        asm("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(t.x), "=r"(t.y), "=r"(t.z), "=r"(t.w) : "l"(p));
-        memcpy(out, &t, 16);
-    } else if constexpr (sizeof(V) * VEC == 8) {
-        uint2 t;
-        asm("ld.global.nc.L1::no_allocate.v2.u32 {%0, %1}, [%2];" : "=r"(t.x), "=r"(t.y) : "l"(p));
-        memcpy(out, &t, 8);
-    } else {
-        unsigned int t;
-        asm("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(t) : "l"(p));
-        memcpy(out, &t, 4);
-    }
-}
+constexpr int kSpmmRot = 17;   // worker rotation per tile
 
 template <typename V>
 struct SpmmArgs {
@@ -165,7 +147,6 @@ struct SpmmArgs {
     V *dot_part;                       // [gridDim.x * k]  (DOT)
     unsigned int *ticket;
     int y_policy;                      // 1: stream Y with L2 evict-first
-    int near_rows;                     // |column - row| beyond this: the dense row is not kept in L1 (0: keep all)
 };
 
 
@@ -227,8 +208,7 @@ __device__ __noinline__ V carry_publish(const int2 *__restrict__ tile_xy, V *til
 //   THREADS     consumer threads (+ one producer warp);  TILE merge items per tile;  STAGES tiles
 //               in flight;  MINB CTAs per SM
 //   DOT         also accumulate X[r,:].Y[r,:] (p.Ap of CG); needs k <= KB (one column block)
-//   NEAR        dense rows of columns farther than near_rows from the diagonal bypass L1 allocation
-template <typename V, int G, int VEC, int NV, int UB, int THREADS, int TILE, int STAGES, int MINB, bool DOT, bool NEAR>
+template <typename V, int G, int VEC, int NV, int UB, int THREADS, int TILE, int STAGES, int MINB, bool DOT>
 __global__ void __launch_bounds__(THREADS + 32, MINB)
 spmm_rows_kernel(SpmmArgs<V> a, CgScalars cg)
 {
@@ -242,8 +222,12 @@ spmm_rows_kernel(SpmmArgs<V> a, CgScalars cg)
 
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ uint64_t s_full[STAGES], s_empty[STAGES];
-    __shared__ V s_wsum[DOT ? NW : 1][DOT ? KB : 1];
-    __shared__ V s_red[THREADS + 32];
+    // the reduction scratch of the DOT epilogue reuses the stage buffers (all tiles are consumed by
+    // then): static shared memory stays at a few bytes, so that 2 stages of 2016 items fit the 64 KB
+    // carve-out and L1 keeps 192 KB for the dense-row gathers
+    static_assert(!DOT || (size_t)(NW * KB + THREADS + 32) * sizeof(V) <= SM::STAGE_BYTES * STAGES, "epilogue scratch");
+    V(*s_wsum)[KB] = reinterpret_cast<V(*)[KB]>(smem_raw);
+    V *s_red = reinterpret_cast<V *>(smem_raw) + NW * KB;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int w = tid / G, li = tid % G;
@@ -316,7 +300,6 @@ spmm_rows_kernel(SpmmArgs<V> a, CgScalars cg)
         const uint64_t pol_y = l2_policy_evict_first();
         const int num_cb = DOT ? 1 : (a.k + KB - 1) / KB;
         const unsigned kbytes = (unsigned)a.k * (unsigned)sizeof(V);   // bytes per dense row
-        const unsigned near2 = 2u * (unsigned)a.near_rows;
         int2 nxt_lo = make_int2(0, 0), nxt_hi = make_int2(0, 0);
         {
             const int t = tile_of(0);
@@ -342,6 +325,10 @@ spmm_rows_kernel(SpmmArgs<V> a, CgScalars cg)
             // in tile t+1); local row 0 may have begun in tile t-1.  Both sides meet in slot t-1 / t.
             const bool has_in = t > 0 && x0 < a.m;
 
+            // rotate the worker -> row map from tile to tile: with rows % W != 0 the same workers would
+            // otherwise take the extra row of every tile
+            const int wrot = (w + it * kSpmmRot) % W;
+
             mbar_wait(&s_full[s], parity);
 
             for (int cb = 0; cb < num_cb; ++cb) {
@@ -356,12 +343,11 @@ spmm_rows_kernel(SpmmArgs<V> a, CgScalars cg)
                     if (!ok[q]) coff[q] = 0;
                     xlane[q] = reinterpret_cast<const char *>(a.X + coff[q]);
                 }
-                for (int i = w; i <= rows; i += W) {
+                for (int i = wrot; i <= rows; i += W) {
                     const int beg0 = (i == 0) ? 0 : s_re[i - 1] - y0;
                     const int end = (i == rows) ? nz : s_re[i] - y0;
                     const bool is_out = (i == rows), is_in = (i == 0) && has_in;
                     if (is_out && hi.x >= a.m) continue;   // behind the last row: nothing to produce
-                    const int grow = x0 + i;
                     V acc[NV][VEC];
 #pragma unroll
                     for (int q = 0; q < NV; ++q)
@@ -384,21 +370,10 @@ spmm_rows_kernel(SpmmArgs<V> a, CgScalars cg)
                         V xv[UB][NV][VEC];
 #pragma unroll
                         for (int u = 0; u < UB; ++u) {      // unconditional: slots behind the row read valid columns
-                            const int col = pcb[u];
-                            const size_t xrow = (size_t)(unsigned)col * kbytes;
-                            if constexpr (NEAR) {
-                                const bool far = (unsigned)(col - grow + a.near_rows) > near2;
+                            const size_t xrow = (size_t)(unsigned)pcb[u] * kbytes;
 #pragma unroll
-                                for (int q = 0; q < NV; ++q) {
-                                    const V *src = reinterpret_cast<const V *>(xlane[q] + xrow);
-                                    if (far) ldg_vec_na<V, VEC>(xv[u][q], src);
-                                    else ldg_vec<V, VEC>(xv[u][q], src);
-                                }
-                            } else {
-#pragma unroll
-                                for (int q = 0; q < NV; ++q)
-                                    ldg_vec<V, VEC>(xv[u][q], reinterpret_cast<const V *>(xlane[q] + xrow));
-                            }
+                            for (int q = 0; q < NV; ++q)
+                                ldg_vec<V, VEC>(xv[u][q], reinterpret_cast<const V *>(xlane[q] + xrow));
                         }
 #pragma unroll
                         for (int u = 0; u < UB; ++u)

@@ -58,6 +58,7 @@ def test_kernel_tile_coordinates_are_the_reference_search(gpu, orc):
     for gen in (lambda: gpu.gen_grid3d(24, True), lambda: gpu.gen_wheel(50000), lambda: gpu.gen_rmat(12, 16)):
         ro, ci, va = gen()
         a = gpu.CsrMatrix(ro, ci, va)
-        coords, items = a.tile_coords(1)
-        assert np.array_equal(coords, orc.merge_partition(ro, len(coords) - 1, items))
+        for k in (1, 8, 32):      # SpMV tiling, and the tiling of whichever SpMM kernel takes (matrix, k)
+            coords, items = a.tile_coords(k)
+            assert np.array_equal(coords, orc.merge_partition(ro, len(coords) - 1, items)), k
         a.close()

@@ -136,3 +136,77 @@ def test_linearity_at_scale(gpu):
     deg = torch.from_numpy(np.diff(ro).astype(np.float64)).cuda() - 1.0
     assert torch.equal(s, 6.0 - deg)
     a.close()
+
+
+def test_spmm_at_scale_matches_column_spmv(gpu):
+    """BASELINE-sized SpMM (200^3 would need 4 GB of blocks; 150^3 x 32 exercises the same
+    round-robin tile deal over all 148 CTAs): every column of A X equals the single-vector product
+    of that column, and A * ones has the exact Poisson row sums."""
+    import torch
+    ro, ci, va = gpu.gen_grid3d(150, True, 6.0, -1.0)
+    n = len(ro) - 1
+    a = gpu.CsrMatrix(ro, ci, va)
+    g = torch.Generator(device="cuda").manual_seed(7)
+    X = torch.rand(n, 32, dtype=torch.float64, device="cuda", generator=g) - 0.5
+    Y = a.spmm(X)
+    Y2 = a.spmm(X)
+    gpu.sync()
+    assert torch.equal(Y, Y2), "SpMM must be deterministic run to run"
+    for c in (0, 13, 31):
+        y = a.spmv(X[:, c].contiguous())
+        gpu.sync()
+        assert (Y[:, c] - y).abs().max().item() <= 1e-12 * 12.0 * 0.5
+    ones = torch.ones(n, 32, dtype=torch.float64, device="cuda")
+    S = a.spmm(ones)
+    gpu.sync()
+    deg = torch.from_numpy(np.diff(ro).astype(np.float64)).cuda() - 1.0
+    assert torch.equal(S, (6.0 - deg)[:, None].expand(n, 32))
+    a.close()
+
+
+ROWS_KERNEL_CHILD = r'''
+import sys
+import numpy as np
+sys.path[:0] = [sys.argv[1], sys.argv[1] + "/tests", sys.argv[1] + "/sparse-matrix-linear-equations_b200/python"]
+import smle_b200 as S
+from oracle import oracle as O
+from conftest import rel_rownorm_err
+orc = O.port()
+S.init(0)
+rng = np.random.default_rng(3)
+def empty_rows(m, n):
+    deg = rng.integers(0, 6, size=m); deg[rng.random(m) < 0.4] = 0; deg[m // 2] = 9000
+    ro = np.concatenate([[0], np.cumsum(deg)]).astype(np.int32)
+    ci = np.concatenate([np.sort(rng.integers(0, n, size=d)) for d in deg]).astype(np.int32)
+    return ro, ci, (rng.random(len(ci)) - 0.5)
+cases = [("wheel", S.gen_wheel(30000)), ("dense", S.gen_dense(40, 3300, 0.5)), ("rmat", S.gen_rmat(12, 16, seed=3)),
+         ("empty_rows", empty_rows(3000, 777)), ("grid", S.gen_grid3d(20, True, 6.0, -1.0))]
+for dtype, tol in ((np.float64, 1e-12), (np.float32, 1e-5)):
+    for name, (ro, ci, va) in cases:
+        va = va.astype(dtype)
+        n = int(ci.max()) + 1
+        for k in (2, 5, 32, 33):
+            X = (rng.random((max(n, len(ro) - 1), k)) - 0.5).astype(dtype)
+            a = S.CsrMatrix(ro, ci, va, X.shape[0])
+            coords, items = a.tile_coords(k)
+            assert items == 1920, (name, k, items)       # the row-per-worker kernel's tiling was used
+            Y = a.spmm(X)
+            err = rel_rownorm_err(Y, orc.merge_csrmm(8, ro, ci, va, X, k, n=X.shape[0]), (ro, ci, va), X)
+            assert err <= tol, (name, k, dtype.__name__, err)
+            assert np.array_equal(Y, a.spmm(X)), (name, k, "not deterministic")
+            a.close()
+print("ROWS_KERNEL_OK")
+'''
+
+
+def test_rows_kernel_on_skewed_matrices(gpu):
+    """The row-per-worker SpMM kernel is only dispatched for matrices without long rows, but its
+    carry exchange is general: forced (SMLE_SPMM_ROWS_MAXLEN) onto wheel / dense / R-MAT / empty-row
+    matrices it must still match the oracle -- rows spanning many tiles exercise the pass-on path."""
+    import os
+    import subprocess
+    import sys
+    from conftest import ROOT
+    env = dict(os.environ, SMLE_SPMM_ROWS_MAXLEN="2000000000")
+    r = subprocess.run([sys.executable, "-c", ROWS_KERNEL_CHILD, str(ROOT)], env=env, capture_output=True, text=True, timeout=600)
+    assert "ROWS_KERNEL_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
