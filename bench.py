@@ -191,6 +191,17 @@ def run_reference_arm(args):
     print(json.dumps(line), flush=True)
 
 
+def ncu_traffic(key):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed
+    `ncu --set full` capture (profiles/roofline_traffic.json names the report it was read from); None
+    when no capture of this workload is committed."""
+    try:
+        rec = json.loads((ROOT / "profiles" / "roofline_traffic.json").read_text())[key]
+        return int(rec["dram_bytes_read"]) + int(rec["dram_bytes_write"])
+    except Exception:
+        return None
+
+
 def workload_config(n, nnz, gpus):
     return {"workload": f"single-RHS CG (cpu_singlecg path) fp64, 3-D 7-point Poisson {GRID}^3 "
                         f"(InitGrid3d(w,true), diag 6 / off-diag -1), RHS srand(42) stream",
@@ -311,9 +322,9 @@ def run_singlecg(args):
                     "h2d_bytes_per_step": L * n * 8, "d2h_bytes_per_step": L * n * 8,
                     "api": "smle_cg_single_f64(host b -> host x), pinned buffers"},
             "gpu_launches": int(launches_all),
-            "roofline": {"bound": "hbm", "kernel": "spmv_kernel<double,256,12,2,DOT> (TMA-staged merge-path SpMV + p.Ap)",
+            "roofline": {"bound": "hbm", "kernel": "spmv_kernel<double,480,6,2,DOT> (TMA-staged merge-path SpMV + p.Ap)",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src,
+                         "traffic": ncu_traffic("spmv_dot_grid3d_150"), "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": k1_bytes,
                          "kernel_ms": {"spmv_dot": kms[0], "update_r_dot": kms[1], "update_xp": kms[2]},
                          "how": "CUDA events around every launch of 40 un-graphed CG iterations on the launch stream",

@@ -443,7 +443,7 @@ int launch_spmv_t(smle_csr_t a, const V *x, V *y, const CgScalars &cg, bool dry)
     return check_launch("spmv_kernel");
 }
 
-constexpr int kSpmvThreads = 256, kSpmvIPT = 12, kSpmvStages = 2;   // default configuration
+constexpr int kSpmvThreads = 480, kSpmvIPT = 6, kSpmvStages = 2;   // default configuration (profiles/r01_spmv_sweeps.txt)
 
 int spmv_cfg()   // threads*10000 + ipt*100 + stages
 {
@@ -466,6 +466,7 @@ int launch_spmv(smle_csr_t a, const V *x, V *y, const CgScalars &cg, bool dry)
 #define SMLE_CFG(th, i, st) case th * 10000 + i * 100 + st: return launch_spmv_t<V, th, i, st, DOT>(a, x, y, cg, dry);
         SMLE_CFG(256, 12, 2) SMLE_CFG(128, 12, 2)
         SMLE_CFG(256, 8, 2) SMLE_CFG(256, 8, 3) SMLE_CFG(224, 12, 2) SMLE_CFG(224, 14, 2) SMLE_CFG(480, 6, 2) SMLE_CFG(480, 7, 2)
+        SMLE_CFG(480, 5, 2) SMLE_CFG(480, 4, 3) SMLE_CFG(960, 3, 2) SMLE_CFG(960, 4, 2) SMLE_CFG(480, 4, 2) SMLE_CFG(960, 2, 3)
 #undef SMLE_CFG
     }
     return fail(SMLE_ERR_ARG, "unsupported SMLE_SPMV_CFG");
