@@ -68,6 +68,40 @@ int check_launch(const char *what)
     return SMLE_OK;
 }
 
+// Kernel launch on g_stream; with g_pdl set (the CG iteration loop) the launch carries the
+// programmatic-stream-serialization attribute, so the kernel may be scheduled while its
+// predecessor drains (smle_common.cuh, griddep_wait).  Captured into CUDA graphs as programmatic edges.
+bool g_pdl = false;
+
+bool pdl_enabled()
+{
+    static int on = -1;
+    if (on < 0) { const char *e = getenv("SMLE_PDL"); on = e ? atoi(e) : 0; }   // measured slower: off
+    return on != 0;
+}
+
+template <typename... KArgs, typename... Args>
+void launch_kernel(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, Args... args)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = g_stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = g_pdl ? 1 : 0;
+    cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);   // errors surface through check_launch()
+}
+
+struct PdlScope {   // CG iteration launches inside this scope use PDL
+    bool prev;
+    PdlScope() : prev(g_pdl) { g_pdl = pdl_enabled(); }
+    ~PdlScope() { g_pdl = prev; }
+};
+
 } // namespace
 
 // =========================================================================================
@@ -241,7 +275,7 @@ int launch_merge_t(smle_csr_t a, const V *X, V *Y, int k, const CgScalars &cg, b
     args.dot_part = (V *)a->dot_part;
     args.fix_part = (V *)a->fix_part;
     args.ticket = a->ticket;
-    merge_kernel<V, G, VEC, IPW, U, DOT><<<dim3(grid, col_blocks), kThreads, 0, g_stream>>>(args, cg);
+    launch_kernel(merge_kernel<V, G, VEC, IPW, U, DOT>, dim3(grid, col_blocks), dim3(kThreads), 0, args, cg);
     ++g_launches;
     return check_launch("merge_kernel");
 }
@@ -318,7 +352,7 @@ int launch_spmm_rows_t(smle_csr_t a, const V *X, V *Y, int k, const CgScalars &c
     static int ypol = -1;
     if (ypol < 0) ypol = env_int("SMLE_SPMM_YPOL", 1);
     args.y_policy = ypol;
-    kern<<<grid, THREADS + 32, smem, g_stream>>>(args, cg);
+    launch_kernel(kern, dim3(grid), dim3(THREADS + 32), smem, args, cg);
     ++g_launches;
     return check_launch("spmm_rows_kernel");
 }
@@ -438,7 +472,7 @@ int launch_spmv_t(smle_csr_t a, const V *x, V *y, const CgScalars &cg, bool dry)
     args.timing = g_timing;
     args.dist = (const DistCtl *)g_spmv_dist;
     { static int dbg = -1; if (dbg < 0) { const char *e = getenv("SMLE_SPMV_DEBUG"); dbg = e ? atoi(e) : 0; } args.debug_flags = dbg; }
-    kern<<<grid, THREADS + 32, smem, g_stream>>>(args, cg);   // + the producer warp
+    launch_kernel(kern, dim3(grid), dim3(THREADS + 32), smem, args, cg);   // + the producer warp
     ++g_launches;
     return check_launch("spmv_kernel");
 }
@@ -613,8 +647,8 @@ template <int G, int VEC>
 int launch_vec_t(int which, const CgVecArgs &va, const CgScalars &cg, int max_iters, double tol, int grid, int seq_base)
 {
     if (which == 0) cg_init_kernel<G, VEC><<<grid, kThreads, 0, g_stream>>>(va, cg, max_iters, tol, seq_base);
-    else if (which == 1) cg_update_r_kernel<G, VEC><<<grid, kThreads, 0, g_stream>>>(va, cg);
-    else cg_update_xp_kernel<G, VEC><<<grid, kThreads, 0, g_stream>>>(va, cg);
+    else if (which == 1) launch_kernel(cg_update_r_kernel<G, VEC>, dim3(grid), dim3(kThreads), 0, va, cg);
+    else launch_kernel(cg_update_xp_kernel<G, VEC>, dim3(grid), dim3(kThreads), 0, va, cg);
     ++g_launches;
     return check_launch("cg vector kernel");
 }
@@ -628,8 +662,18 @@ int launch_vec(int which, const CgVecArgs &va, const CgScalars &cg, int max_iter
         long long want = ((long long)(va.n >> 1) + kThreads * kVecUnroll - 1) / (kThreads * kVecUnroll);
         int grid = (int)(want < (long long)g_sms * ctas_per_sm ? want : (long long)g_sms * ctas_per_sm);
         if (grid < 1) grid = 1;
-        if (which == 1) cg1_update_r_kernel<<<grid, kThreads, 0, g_stream>>>(va, cg);
-        else cg1_update_xp_kernel<<<grid, kThreads, 0, g_stream>>>(va, cg);
+        // Under PDL these CTAs are scheduled while K1's CTAs drain one by one: without a limit the first
+        // SMs to free up would swallow eight of them each.  An (unused) dynamic shared-memory request
+        // pins the residency at ctas_per_sm, so the grid spreads evenly however early it arrives.
+        static size_t pin = 0;
+        if (!pin) {
+            pin = ((size_t)227 * 1024 / (size_t)(ctas_per_sm > 0 ? ctas_per_sm : 1) - 2048) & ~(size_t)1023;
+            CU(cudaFuncSetAttribute(cg1_update_r_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pin));
+            CU(cudaFuncSetAttribute(cg1_update_xp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pin));
+        }
+        const size_t smem_pin = g_pdl ? pin : 0;
+        if (which == 1) launch_kernel(cg1_update_r_kernel, dim3(grid), dim3(kThreads), smem_pin, va, cg);
+        else launch_kernel(cg1_update_xp_kernel, dim3(grid), dim3(kThreads), smem_pin, va, cg);
         ++g_launches;
         return check_launch("cg1 vector kernel");
     }
@@ -648,6 +692,7 @@ int launch_vec(int which, const CgVecArgs &va, const CgScalars &cg, int max_iter
 
 int launch_iteration(smle_csr_t a, const CgVecArgs &va, const CgScalars &cg)
 {
+    PdlScope pdl;
     int rc = launch_merge<double, true>(a, va.P, va.AP, va.k, cg);
     if (!rc) rc = launch_vec(1, va, cg);
     if (!rc) rc = launch_vec(2, va, cg);

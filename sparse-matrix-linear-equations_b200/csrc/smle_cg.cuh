@@ -169,6 +169,8 @@ cg_update_r_kernel(CgVecArgs a, CgScalars cg)
     __shared__ double s_w[kWarps][KB];
     __shared__ double s_red[kThreads];
     __shared__ int s_cnt[kThreads];
+    griddep_wait();
+    griddep_launch_dependents();
     if (cg.ctrl[CTRL_STOP]) return;
     const int tid = threadIdx.x, w = tid / G, li = tid % G;
     const size_t k = (size_t)a.k;
@@ -209,6 +211,8 @@ __global__ void __launch_bounds__(kThreads)
 cg_update_xp_kernel(CgVecArgs a, CgScalars cg)
 {
     constexpr int W = kThreads / G, KB = G * VEC;
+    griddep_wait();
+    griddep_launch_dependents();
     if (cg.ctrl[CTRL_HALT]) return;
     const bool final_iter = cg.ctrl[CTRL_STOP] != 0;
     const int tid = threadIdx.x, w = tid / G, li = tid % G;
@@ -250,6 +254,8 @@ cg1_update_r_kernel(CgVecArgs a, CgScalars cg)
 {
     __shared__ double s_red[kThreads];
     __shared__ int s_cnt[kThreads];
+    griddep_wait();
+    griddep_launch_dependents();
     if (cg.ctrl[CTRL_STOP]) return;
     const int tid = threadIdx.x;
     const uint64_t pol_first = make_policy_evict_first(), pol_last = make_policy_evict_last();
@@ -301,6 +307,8 @@ cg1_update_r_kernel(CgVecArgs a, CgScalars cg)
 __global__ void __launch_bounds__(kThreads)
 cg1_update_xp_kernel(CgVecArgs a, CgScalars cg)
 {
+    griddep_wait();
+    griddep_launch_dependents();
     if (cg.ctrl[CTRL_HALT]) return;
     const bool final_iter = cg.ctrl[CTRL_STOP] != 0;
     const int tid = threadIdx.x;

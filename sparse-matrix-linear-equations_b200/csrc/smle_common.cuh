@@ -161,6 +161,17 @@ __device__ __forceinline__ void st_f64_hint(double *p, double v, uint64_t pol)
 }
 
 // ---------------------------------------------------------------------------------------
+// Programmatic dependent launch (PDL).  The three kernels of a CG iteration are launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization, inside the CUDA graph too: kernel n+1 is
+// scheduled onto the SMs while the tail of kernel n (its last CTA's serial epilogue) still runs,
+// and blocks in griddep_wait() until kernel n has completed and its writes are visible.  Every
+// kernel triggers its dependents only AFTER its own wait, so when a kernel starts, everything
+// two launches back is complete.  Both are no-ops for launches without the attribute.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+// ---------------------------------------------------------------------------------------
 // "last CTA done" election (threadFenceReduction pattern): every CTA publishes its global
 // writes, takes a ticket, and the CTA that draws the last ticket runs the serial epilogue
 // (carry fix-up, deterministic reduction of the per-CTA partials, CG scalars).  The ticket

@@ -110,9 +110,12 @@ merge_kernel(MergeArgs<V> a, CgScalars cg)
         // CG graph: once the stop flag is up this launch is a no-op; the first SpMM after
         // the final x update raises HALT so the trailing update kernels no-op as well.
         if (cg.ctrl[CTRL_STOP]) {
+            griddep_wait();
             if (blockIdx.x == 0 && blockIdx.y == 0 && tid == 0) cg.ctrl[CTRL_HALT] = 1;
             return;
         }
+        griddep_wait();
+        griddep_launch_dependents();
     }
 
     const size_t k = (size_t)a.k;

@@ -234,7 +234,8 @@ spmm_rows_kernel(SpmmArgs<V> a, CgScalars cg)
     const size_t k = (size_t)a.k;
 
     if constexpr (DOT) {
-        if (cg.ctrl[CTRL_STOP]) {
+        if (cg.ctrl[CTRL_STOP]) {      // see spmv_kernel: STOP is two launches old, HALT waits for K3
+            griddep_wait();
             if (blockIdx.x == 0 && tid == 0) cg.ctrl[CTRL_HALT] = 1;
             return;
         }
@@ -297,6 +298,7 @@ spmm_rows_kernel(SpmmArgs<V> a, CgScalars cg)
         }
     } else {
         // =============================== consumer warps ==========================================
+        if constexpr (DOT) { griddep_wait(); griddep_launch_dependents(); }   // the producer already streams A
         const uint64_t pol_y = l2_policy_evict_first();
         const int num_cb = DOT ? 1 : (a.k + KB - 1) / KB;
         const unsigned kbytes = (unsigned)a.k * (unsigned)sizeof(V);   // bytes per dense row

@@ -243,7 +243,10 @@ spmv_kernel(SpmvArgs<V> a, CgScalars cg)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
     if constexpr (DOT) {
+        // STOP was written two launches back (K2): complete by now, see griddep_wait().  HALT is read
+        // by the K3 that may still be running, so it is raised only after that kernel has finished.
         if (cg.ctrl[CTRL_STOP]) {
+            griddep_wait();
             if (blockIdx.x == 0 && tid == 0) cg.ctrl[CTRL_HALT] = 1;
             return;
         }
@@ -297,6 +300,9 @@ spmv_kernel(SpmvArgs<V> a, CgScalars cg)
         }
     } else {
         // =============================== consumer warps ==========================================
+        // The producer above streams the (immutable) matrix right away; x and y belong to the previous
+        // kernel until it has completed.
+        if constexpr (DOT) { griddep_wait(); griddep_launch_dependents(); }
         // tile metadata is fetched one tile ahead so its latency hides behind the previous tile
         int2 nxt_lo = make_int2(0, 0), nxt_hi = make_int2(0, 0);
         int nxt_ml = 0;

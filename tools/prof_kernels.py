@@ -1,5 +1,5 @@
 """Small driver for ncu: runs the hot kernels a few times on a BASELINE-sized input.
-usage: python tools/prof_kernels.py {spmv|spmm32|cg|cgmulti} [grid_width]"""
+usage: python tools/prof_kernels.py {spmv|spmm<k>|cg|cgmulti|rmat<k>|wheel<k>|grid2d} [grid_width or scale]"""
 import sys
 from pathlib import Path
 
@@ -13,7 +13,17 @@ w = int(sys.argv[2]) if len(sys.argv) > 2 else 150
 S.init(0)
 st = torch.cuda.Stream()
 S.set_stream(st.cuda_stream)
-ro, ci, va = S.gen_grid3d(w, True, 6.0, -1.0)
+if what.startswith("rmat"):      # rmat<k>: R-MAT scale w, 16 edges per vertex
+    ro, ci, va = S.gen_rmat(w, 16, seed=42)
+    what = ("spmm" + what[4:]) if what[4:] not in ("", "1") else "spmv"
+elif what.startswith("wheel"):
+    ro, ci, va = S.gen_wheel(1 << w)
+    what = ("spmm" + what[5:]) if what[5:] not in ("", "1") else "spmv"
+elif what.startswith("grid2d"):
+    ro, ci, va = S.gen_grid2d(w, True)
+    what = "spmv"
+else:
+    ro, ci, va = S.gen_grid3d(w, True, 6.0, -1.0)
 n = len(ro) - 1
 a = S.CsrMatrix(ro, ci, va)
 with torch.cuda.stream(st):
