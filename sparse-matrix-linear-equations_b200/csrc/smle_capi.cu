@@ -1140,8 +1140,8 @@ int dist_launch_iteration(smle_dist_t d, const CgVecArgs &va, const CgScalars &c
     const int grid = dist_vec_grid(va.n);
     cg1d_update_r_kernel<<<grid, kThreads, 0, g_stream>>>(va, cg, d->ctl);
     cg1d_update_xp_kernel<<<grid, kThreads, 0, g_stream>>>(va, cg, d->ctl, 0);
-    dist_halo_push_kernel<<<dist_push_grid(d), kThreads, 0, g_stream>>>(d->ctl, va.P, cg.ctrl);
-    g_launches += 3;
+    if (!d->ctl.fused) dist_halo_push_kernel<<<dist_push_grid(d), kThreads, 0, g_stream>>>(d->ctl, va.P, cg.ctrl);
+    g_launches += d->ctl.fused ? 2 : 3;
     return check_launch("distributed CG iteration");
 }
 
@@ -1179,6 +1179,23 @@ int smle_dist_create(smle_dist_t *out, smle_csr_t local_a, int rank, int world, 
     for (int q = 0; q <= world; ++q) c.send_off[q] = send_off[q];
     for (int q = 0; q < world; ++q) { c.send_dst[q] = send_dst[q]; c.needs_from[q] = needs_from[q]; }
     c.ticket = d->ticket;
+    {   // fused push: possible when every send group is one ascending run of consecutive local rows
+        static int allow = -1;
+        if (allow < 0) { const char *e = getenv("SMLE_DIST_FUSED_PUSH"); allow = e ? atoi(e) : 1; }
+        c.fused = allow;
+        c.npush = 0;
+        for (int q = 0; q < world && c.fused; ++q) {
+            const int cnt = send_off[q + 1] - send_off[q];
+            if (cnt <= 0) continue;
+            for (int i = 1; i < cnt; ++i)
+                if (send_idx[send_off[q] + i] != send_idx[send_off[q]] + i) { c.fused = 0; break; }
+            c.push_q[c.npush] = q;
+            c.push_lo[c.npush] = send_idx[send_off[q]];
+            c.push_cnt[c.npush] = cnt;
+            ++c.npush;
+        }
+        if (!c.fused) c.npush = 0;
+    }
     c.peer[rank] = c.self;
     c.peer_p[rank] = dist_p(d);
     d->peer_base[rank] = d->comm;
@@ -1288,7 +1305,7 @@ int smle_dist_cg_f64(smle_dist_t d, const double *b_local_dev, double *x_local_d
         CU(cudaStreamBeginCapture(g_stream, cudaStreamCaptureModeThreadLocal));
         for (int i = 0; i < kGraphIters && !rc; ++i) rc = dist_launch_iteration(d, va, cg);
         cudaError_t e = cudaStreamEndCapture(g_stream, &graph);
-        g_launches -= 4LL * kGraphIters;
+        g_launches -= (d->ctl.fused ? 3LL : 4LL) * kGraphIters;
         if (rc) return rc;
         if (e != cudaSuccess) return fail(SMLE_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(e));
         e = cudaGraphInstantiate(&d->graph, graph, 0);
@@ -1302,7 +1319,7 @@ int smle_dist_cg_f64(smle_dist_t d, const double *b_local_dev, double *x_local_d
     auto submit = [&](int slot) -> int {
         if (use_graph) {
             CU(cudaGraphLaunch(d->graph, g_stream));
-            g_launches += 4LL * batch;
+            g_launches += (d->ctl.fused ? 3LL : 4LL) * batch;
         } else {
             for (int i = 0; i < batch; ++i) {
                 int r2 = dist_launch_iteration(d, va, cg);

@@ -101,11 +101,12 @@ __global__ void __launch_bounds__(kThreads)
 cg1d_update_xp_kernel(CgVecArgs a, CgScalars cg, DistCtl d, int mode)
 {
     __shared__ double s_rr, s_beta;
-    __shared__ int s_final;
+    __shared__ int s_final, s_it;
     if (cg.ctrl[CTRL_STOP]) return;
     const int tid = threadIdx.x;
     if (tid == 0) {
         const int it = cg.ctrl[CTRL_ITER];
+        s_it = it;
         if (mode == 1) {
             s_rr = dist_wait_sum(d, 2, 0, (unsigned long long)cg.ctrl[CTRL_SEQ_BASE] + 1ull);
             s_beta = 0.0;
@@ -147,6 +148,15 @@ cg1d_update_xp_kernel(CgVecArgs a, CgScalars cg, DistCtl d, int mode)
                         p[u].x = r[u].x + be * p[u].x;
                         p[u].y = r[u].y + be * p[u].y;
                         st_f64x2_hint(a.P + 2 * j, p[u], pol_last);
+                        if (d.fused) {
+                            // rows on this rank's boundary go straight into the neighbours' halo tails (NVLink)
+                            for (int g = 0; g < d.npush; ++g) {
+                                const int off = (int)(2 * j) - d.push_lo[g];
+                                double *dst = d.peer_p[d.push_q[g]] + d.send_dst[d.push_q[g]];
+                                if ((unsigned)off < (unsigned)d.push_cnt[g]) dst[off] = p[u].x;
+                                if ((unsigned)(off + 1) < (unsigned)d.push_cnt[g]) dst[off + 1] = p[u].y;
+                            }
+                        }
                     }
                 }
             }
@@ -155,10 +165,30 @@ cg1d_update_xp_kernel(CgVecArgs a, CgScalars cg, DistCtl d, int mode)
             const int j = a.n - 1;
             const double pj = a.P[j];
             a.X[j] += al * pj;
-            if (!final_iter) a.P[j] = a.R[j] + be * pj;
+            if (!final_iter) {
+                const double pn = a.R[j] + be * pj;
+                a.P[j] = pn;
+                if (d.fused)
+                    for (int g = 0; g < d.npush; ++g) {
+                        const int off = j - d.push_lo[g];
+                        if ((unsigned)off < (unsigned)d.push_cnt[g]) d.peer_p[d.push_q[g]][d.send_dst[d.push_q[g]] + off] = pn;
+                    }
+            }
         }
+        if (d.fused && !final_iter) __threadfence_system();   // peer stores ordered before the sequence numbers
     }
     if (!last_cta_election(a.ticket, gridDim.x)) return;
+    if (mode == 0 && d.fused && !s_final) {
+        // halo of the p for iteration it+1: tell the neighbours, then wait for theirs, so that the next
+        // SpMV starts (kernel boundary) with a complete halo
+        const unsigned long long seq = (unsigned long long)cg.ctrl[CTRL_SEQ_BASE] + (unsigned long long)s_it + 2ull;
+        const int q = tid;
+        if (q < d.world && q != d.rank) {
+            if (d.send_off[q + 1] > d.send_off[q]) st_release_sys(&d.peer[q]->halo_seq[d.rank], seq);
+            if (d.needs_from[q]) dist_spin(&d.self->halo_seq[q], seq, &d.self->error);
+        }
+        __syncthreads();
+    }
     if (tid == 0) {
         if (mode == 1) {
             const double nb = sqrt(s_rr);

@@ -28,6 +28,13 @@ struct DistCtl {
     int send_dst[kMaxRanks];            // element offset in the peer's p vector where my group lands
     int needs_from[kMaxRanks];          // 1 when this rank receives halo entries from peer q
     unsigned int *ticket;
+    // fused halo push (every send group is one contiguous run of local rows, e.g. the boundary planes
+    // of a slab): K3 stores the new p of those rows straight into the neighbours' halo tails
+    int fused;                          // 1: K3 pushes, no separate push kernel inside the iteration
+    int npush;                          // peers with a non-empty group
+    int push_q[kMaxRanks];              // their ranks
+    int push_lo[kMaxRanks];             // first local row of the group
+    int push_cnt[kMaxRanks];            // rows in the group
 };
 
 __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p)

@@ -58,14 +58,17 @@ def _worker(rank, world, port, w, q):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world", [2])
-def test_row_partitioned_spmv_and_cg(gpu, world):
+@pytest.mark.parametrize("world,fused", [(2, 1), (2, 0), (4, 1), (8, 1)])
+def test_row_partitioned_spmv_and_cg(gpu, world, fused, monkeypatch):
+    """fused = 1: K3 stores the boundary rows of the new p straight into the neighbours' halo tails;
+    fused = 0: the separate halo push kernel (the path matrices with scattered send lists take)."""
     if gpu.device_count() < world:
         pytest.skip(f"needs {world} GPUs")
     import torch.multiprocessing as mp
+    monkeypatch.setenv("SMLE_DIST_FUSED_PUSH", str(fused))
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    procs = [ctx.Process(target=_worker, args=(r, world, 29700 + world, 40, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, 29700 + 10 * world + fused, 40, q)) for r in range(world)]
     for p in procs:
         p.start()
     res = sorted(q.get(timeout=300) for _ in range(world))
