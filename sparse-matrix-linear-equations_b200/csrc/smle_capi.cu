@@ -338,9 +338,11 @@ int launch_spmm_rows_t(smle_csr_t a, const V *X, V *Y, int k, const CgScalars &c
     int grid = g_sms * occ;
     if (grid > a->max_ctas) grid = a->max_ctas;
     if (grid > p->num_tiles) grid = p->num_tiles;
-    static int chunk_env = -1;
-    if (chunk_env < 0) chunk_env = env_int("SMLE_SPMM_CHUNK", 2);
-    int chunk = chunk_env > 0 ? chunk_env : (p->num_tiles + grid - 1) / grid;
+    // consecutive tiles per deal: 1 everywhere except the 16-lane shape (k = 32 fp64 / 64 fp32), where 2
+    // measured 5 % faster (profiles/r01_spmm_sweeps.txt); SMLE_SPMM_CHUNK overrides, 0 = contiguous runs
+    static int chunk_env = -2;
+    if (chunk_env == -2) chunk_env = env_int("SMLE_SPMM_CHUNK", -1);
+    int chunk = chunk_env > 0 ? chunk_env : (chunk_env == 0 ? (p->num_tiles + grid - 1) / grid : (G == 16 ? 2 : 1));
     SpmmArgs<V> args;
     args.ro = a->ro; args.ci = a->ci; args.va = (const V *)a->va;
     args.X = X; args.Y = Y; args.tile_xy = p->xy;
@@ -375,7 +377,7 @@ long long spmm_cfg()
     return cfg;
 }
 
-constexpr int kSpmmTile = 1920;
+constexpr int kSpmmTile = 1920, kSpmmTileNarrow = 1440;
 
 // G, VEC as picked by pick_shape.  Default configuration (sweeps in profiles/r01_spmm_sweeps.txt):
 // ONE CTA of 30 consumer warps + producer per SM (64 registers per thread; ptxas keeps ~4 dense-row
@@ -406,13 +408,20 @@ int launch_spmm_rows(smle_csr_t a, const V *X, V *Y, int k, const CgScalars &cg,
     }
     if (G == 32 && k > G * VEC)
         return launch_spmm_rows_t<V, G, VEC, 2, kSpmmUB, kSpmmThreads, kSpmmTile, kSpmmStages, 1, DOT>(a, X, Y, k, cg, dry);
+    // narrow blocks: a tile of 1920 items has ~240 rows, so 960 threads of G <= 2 lanes per row would
+    // mostly idle; smaller CTAs, more of them per SM, keep the same number of rows in flight
+    if constexpr (G <= 2)
+        return launch_spmm_rows_t<V, G, VEC, 1, kSpmmUB, 224, kSpmmTileNarrow, kSpmmStages, 4, DOT>(a, X, Y, k, cg, dry);
+    if constexpr (G <= 8)
+        return launch_spmm_rows_t<V, G, VEC, 1, kSpmmUB, 480, kSpmmTile, kSpmmStages, 2, DOT>(a, X, Y, k, cg, dry);
     return launch_spmm_rows_t<V, G, VEC, 1, kSpmmUB, kSpmmThreads, kSpmmTile, kSpmmStages, 1, DOT>(a, X, Y, k, cg, dry);
 }
 
-int spmm_tile_items()
+int spmm_tile_items(int G)
 {
     const long long cfg = spmm_cfg();
-    return cfg ? (int)((cfg / 100000) % 10000) : kSpmmTile;
+    if (cfg && G == 16) return (int)((cfg / 100000) % 10000);
+    return G <= 2 ? kSpmmTileNarrow : kSpmmTile;
 }
 
 // does the row-per-worker kernel take this (matrix, k)?   G, VEC: the shape pick_shape chose
@@ -425,7 +434,7 @@ int spmm_use_rows(smle_csr_t a, int G, int VEC, int k, bool dot, bool *use)
     static int maxlen = -1;
     if (maxlen < 0) maxlen = env_int("SMLE_SPMM_ROWS_MAXLEN", kSpmmRowsMaxLen);
     Partition *p;
-    int rc = get_partition(a, spmm_tile_items(), &p);
+    int rc = get_partition(a, spmm_tile_items(G), &p);
     if (rc) return rc;
     *use = p->max_len <= maxlen;
     return SMLE_OK;
@@ -994,7 +1003,7 @@ int smle_csr_tile_coords(smle_csr_t a, int k, int *num_tiles, int *items_per_til
         bool rows_kernel = false;
         rc = spmm_use_rows(a, G, VEC, k, false, &rows_kernel);
         if (rc) return rc;
-        items = rows_kernel ? spmm_tile_items() : kTileItems;
+        items = rows_kernel ? spmm_tile_items(G) : kTileItems;
     }
     Partition *p;
     rc = get_partition(a, items, &p);

@@ -189,7 +189,7 @@ for dtype, tol in ((np.float64, 1e-12), (np.float32, 1e-5)):
             X = (rng.random((max(n, len(ro) - 1), k)) - 0.5).astype(dtype)
             a = S.CsrMatrix(ro, ci, va, X.shape[0])
             coords, items = a.tile_coords(k)
-            assert items == 1920, (name, k, items)       # the row-per-worker kernel's tiling was used
+            assert items in (1920, 1440), (name, k, items)   # the row-per-worker kernel's tilings
             Y = a.spmm(X)
             err = rel_rownorm_err(Y, orc.merge_csrmm(8, ro, ci, va, X, k, n=X.shape[0]), (ro, ci, va), X)
             assert err <= tol, (name, k, dtype.__name__, err)
