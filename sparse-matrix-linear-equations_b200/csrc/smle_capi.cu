@@ -395,11 +395,8 @@ int launch_spmm_rows(smle_csr_t a, const V *X, V *Y, int k, const CgScalars &cg,
         if (cfg != 0) {
 #define SMLE_CFG(th, tl, st, mb, ub, nv) \
     if (cfg == spmm_cfg_id(th, tl, st, mb, ub, nv)) return launch_spmm_rows_t<V, G / nv, VEC, nv, ub, th, tl, st, mb, DOT>(a, X, Y, k, cg, dry);
-            SMLE_CFG(480, 1024, 2, 2, 4, 1) SMLE_CFG(224, 512, 2, 4, 4, 1) SMLE_CFG(480, 2048, 2, 2, 4, 1)
-            SMLE_CFG(960, 2048, 2, 1, 4, 1) SMLE_CFG(960, 1024, 2, 1, 4, 1) SMLE_CFG(960, 4096, 2, 1, 4, 1)
-            SMLE_CFG(960, 3072, 2, 1, 4, 1) SMLE_CFG(960, 2048, 3, 1, 4, 1) SMLE_CFG(960, 2048, 2, 1, 3, 1)
-            SMLE_CFG(960, 2000, 2, 1, 4, 1) SMLE_CFG(960, 1920, 2, 1, 4, 1) SMLE_CFG(960, 1440, 2, 1, 4, 1)
-            SMLE_CFG(960, 1536, 2, 1, 4, 1) SMLE_CFG(960, 1920, 2, 1, 8, 1) SMLE_CFG(960, 2000, 2, 1, 8, 1) SMLE_CFG(960, 1920, 2, 1, 6, 1)
+            SMLE_CFG(960, 1920, 2, 1, 4, 1) SMLE_CFG(960, 2048, 2, 1, 4, 1) SMLE_CFG(960, 1920, 2, 1, 8, 1)
+            SMLE_CFG(480, 2048, 2, 2, 4, 1) SMLE_CFG(224, 512, 2, 4, 4, 1) SMLE_CFG(960, 1920, 2, 1, 4, 2)
 #undef SMLE_CFG
             return fail(SMLE_ERR_ARG, "unsupported SMLE_SPMM_CFG");
         }
@@ -507,9 +504,7 @@ int launch_spmv(smle_csr_t a, const V *x, V *y, const CgScalars &cg, bool dry)
 {
     switch (spmv_cfg()) {
 #define SMLE_CFG(th, i, st) case th * 10000 + i * 100 + st: return launch_spmv_t<V, th, i, st, DOT>(a, x, y, cg, dry);
-        SMLE_CFG(256, 12, 2) SMLE_CFG(128, 12, 2)
-        SMLE_CFG(256, 8, 2) SMLE_CFG(256, 8, 3) SMLE_CFG(224, 12, 2) SMLE_CFG(224, 14, 2) SMLE_CFG(480, 6, 2) SMLE_CFG(480, 7, 2)
-        SMLE_CFG(480, 5, 2) SMLE_CFG(480, 4, 3) SMLE_CFG(960, 3, 2) SMLE_CFG(960, 4, 2) SMLE_CFG(480, 4, 2) SMLE_CFG(960, 2, 3)
+        SMLE_CFG(480, 6, 2) SMLE_CFG(480, 5, 2) SMLE_CFG(480, 7, 2) SMLE_CFG(256, 12, 2) SMLE_CFG(224, 8, 2) SMLE_CFG(960, 4, 2)
 #undef SMLE_CFG
     }
     return fail(SMLE_ERR_ARG, "unsupported SMLE_SPMV_CFG");

@@ -32,6 +32,15 @@ with torch.cuda.stream(st):
         y = torch.empty_like(x)
         for _ in range(5):
             a.spmv(x, out=y)
+        import os
+        if os.environ.get("PROF_TIME"):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(st)
+            for _ in range(20):
+                a.spmv(x, out=y)
+            e1.record(st)
+            torch.cuda.synchronize()
+            print(f"spmv {what} {w} cfg={os.environ.get('SMLE_SPMV_CFG', 'default')}: {e0.elapsed_time(e1) / 20 * 1e3:.1f} us")
     elif what.startswith("spmm"):
         k = int(what[4:])
         X = torch.rand(n, k, dtype=torch.float64, device="cuda")
