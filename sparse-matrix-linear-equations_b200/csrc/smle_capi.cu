@@ -662,7 +662,7 @@ int launch_vec(int which, const CgVecArgs &va, const CgScalars &cg, int max_iter
     if (va.k == 1 && which != 0 && getenv("SMLE_VEC_GENERIC") == nullptr) {
         // single right-hand side: 128-bit, unrolled kernels with L2 eviction priorities
         static int ctas_per_sm = -1;
-        if (ctas_per_sm < 0) { const char *e = getenv("SMLE_VEC_CTAS"); ctas_per_sm = e ? atoi(e) : 2; }
+        if (ctas_per_sm < 0) { const char *e = getenv("SMLE_VEC_CTAS"); ctas_per_sm = e ? atoi(e) : 3; }
         long long want = ((long long)(va.n >> 1) + kThreads * kVecUnroll - 1) / (kThreads * kVecUnroll);
         int grid = (int)(want < (long long)g_sms * ctas_per_sm ? want : (long long)g_sms * ctas_per_sm);
         if (grid < 1) grid = 1;
@@ -670,8 +670,8 @@ int launch_vec(int which, const CgVecArgs &va, const CgScalars &cg, int max_iter
         // SMs to free up would swallow eight of them each.  An (unused) dynamic shared-memory request
         // pins the residency at ctas_per_sm, so the grid spreads evenly however early it arrives.
         static size_t pin = 0;
-        if (!pin) {
-            pin = ((size_t)227 * 1024 / (size_t)(ctas_per_sm > 0 ? ctas_per_sm : 1) - 2048) & ~(size_t)1023;
+        if (!pin && g_pdl) {
+            pin = ((size_t)227 * 1024 / (size_t)(ctas_per_sm > 0 ? ctas_per_sm : 1) - 8192) & ~(size_t)1023;
             CU(cudaFuncSetAttribute(cg1_update_r_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pin));
             CU(cudaFuncSetAttribute(cg1_update_xp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pin));
         }

@@ -356,13 +356,6 @@ spmm_rows_kernel(SpmmArgs<V> a, CgScalars cg)
 #pragma unroll
                         for (int v = 0; v < VEC; ++v) acc[q][v] = 0;
                     V xr[NV][VEC];
-                    if constexpr (DOT) {
-                        if (!is_out) {
-#pragma unroll
-                            for (int q = 0; q < NV; ++q)
-                                ldg_vec<V, VEC>(xr[q], reinterpret_cast<const V *>(xlane[q] + (size_t)(unsigned)(x0 + i) * kbytes));
-                        }
-                    }
                     for (int beg = beg0; beg < end; beg += UB) {
                         // UB dense rows requested per pass; ptxas keeps about as many loads in flight per
                         // warp as it has scoreboards, the rest of the latency is hidden by the other warps
@@ -386,6 +379,15 @@ spmm_rows_kernel(SpmmArgs<V> a, CgScalars cg)
 #pragma unroll
                                     for (int v = 0; v < VEC; ++v) acc[q][v] += av * xv[u][q][v];
                             }
+                    }
+                    if constexpr (DOT) {
+                        // the row's own dense row was just gathered for the diagonal entry: an L1 hit now,
+                        // and it did not occupy one of the few load slots while the gathers were in flight
+                        if (!is_out) {
+#pragma unroll
+                            for (int q = 0; q < NV; ++q)
+                                ldg_vec<V, VEC>(xr[q], reinterpret_cast<const V *>(xlane[q] + (size_t)(unsigned)(x0 + i) * kbytes));
+                        }
                     }
                     if (is_in || is_out) {
 #pragma unroll

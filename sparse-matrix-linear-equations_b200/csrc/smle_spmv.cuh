@@ -106,7 +106,7 @@ struct SpmvArgs {
     V *fix_part;                       // [gridDim.x]  (DOT)
     unsigned int *ticket;
     long long *timing;                 // debug counters (only read with -DSMLE_TIMING)
-    int debug_flags;                   // 1: skip compute (stream-only ceiling), 2: skip gathers
+    int debug_flags;                   // 1: skip compute (stream-only ceiling of the TMA pipeline)
     const DistCtl *dist;               // row-partitioned CG: post the local p.Ap to every peer (else NULL)
 };
 
@@ -336,11 +336,13 @@ spmv_kernel(SpmvArgs<V> a, CgScalars cg)
                 for (int i = tid; i <= rows; i += THREADS) {
                     const int beg = (i == 0) ? 0 : s_re[i - 1] - y0;
                     const int end = (i == rows) ? nz : s_re[i] - y0;
+                    const V sum = row_sum<V>(a.x, pc, pv, beg, end);
                     V xr = 0;
                     if constexpr (DOT) {
+                        // after the gathers: x[row] was just fetched for the diagonal entry (an L1 hit) and the
+                        // load does not take one of the few load slots while the gathers are in flight
                         if (i < rows) xr = __ldg(a.x + x0 + i);
                     }
-                    const V sum = row_sum<V>(a.x, pc, pv, beg, end);
                     if (i < rows) {
                         a.y[x0 + i] = sum;
                         if constexpr (DOT) dot += sum * xr;
