@@ -354,6 +354,9 @@ int launch_spmm_rows_t(smle_csr_t a, const V *X, V *Y, int k, const CgScalars &c
     static int ypol = -1;
     if (ypol < 0) ypol = env_int("SMLE_SPMM_YPOL", 1);
     args.y_policy = ypol;
+    static int dot_late = -1;
+    if (dot_late < 0) dot_late = env_int("SMLE_SPMM_DOT_LATE", 1);
+    args.dot_late = dot_late;
     launch_kernel(kern, dim3(grid), dim3(THREADS + 32), smem, args, cg);
     ++g_launches;
     return check_launch("spmm_rows_kernel");

@@ -147,6 +147,9 @@ struct SpmmArgs {
     V *dot_part;                       // [gridDim.x * k]  (DOT)
     unsigned int *ticket;
     int y_policy;                      // 1: stream Y with L2 evict-first
+    int dot_late;                      // DOT: load X[row,:] after the gathers (1, default) or before them (0).  Kept as a
+                                       // run-time switch on purpose: with the early load compiled out ptxas keeps only 2
+                                       // gathers in flight instead of 4 (1.61 ms vs 1.42 ms; tests/test_sass_shape.py)
 };
 
 
@@ -356,6 +359,13 @@ spmm_rows_kernel(SpmmArgs<V> a, CgScalars cg)
 #pragma unroll
                         for (int v = 0; v < VEC; ++v) acc[q][v] = 0;
                     V xr[NV][VEC];
+                    if constexpr (DOT) {
+                        if (!is_out && !a.dot_late) {
+#pragma unroll
+                            for (int q = 0; q < NV; ++q)
+                                ldg_vec<V, VEC>(xr[q], reinterpret_cast<const V *>(xlane[q] + (size_t)(unsigned)(x0 + i) * kbytes));
+                        }
+                    }
                     for (int beg = beg0; beg < end; beg += UB) {
                         // UB dense rows requested per pass; ptxas keeps about as many loads in flight per
                         // warp as it has scoreboards, the rest of the latency is hidden by the other warps
@@ -383,7 +393,7 @@ spmm_rows_kernel(SpmmArgs<V> a, CgScalars cg)
                     if constexpr (DOT) {
                         // the row's own dense row was just gathered for the diagonal entry: an L1 hit now,
                         // and it did not occupy one of the few load slots while the gathers were in flight
-                        if (!is_out) {
+                        if (!is_out && a.dot_late) {
 #pragma unroll
                             for (int q = 0; q < NV; ++q)
                                 ldg_vec<V, VEC>(xr[q], reinterpret_cast<const V *>(xlane[q] + (size_t)(unsigned)(x0 + i) * kbytes));
