@@ -35,7 +35,6 @@ cudaStream_t g_stream = nullptr;       // the stream in use (own or caller's)
 int g_device = -1;
 int g_sms = 0;
 long long g_launches = 0;
-long long *g_timing = nullptr;   // device debug counters (SMLE_TIMING builds)
 const void *g_spmv_dist = nullptr;   // device DistCtl of the row-partitioned solve being launched
 
 int fail(int code, const char *fmt, ...)
@@ -478,7 +477,6 @@ int launch_spmv_t(smle_csr_t a, const V *x, V *y, const CgScalars &cg, bool dry)
     args.carry_row = a->carry_row; args.carry_val = (V *)a->carry_val;
     args.dot_part = (V *)a->dot_part; args.fix_part = (V *)a->fix_part;
     args.ticket = a->ticket;
-    args.timing = g_timing;
     args.dist = (const DistCtl *)g_spmv_dist;
     { static int dbg = -1; if (dbg < 0) { const char *e = getenv("SMLE_SPMV_DEBUG"); dbg = e ? atoi(e) : 0; } args.debug_flags = dbg; }
     launch_kernel(kern, dim3(grid), dim3(THREADS + 32), smem, args, cg);   // + the producer warp
@@ -706,6 +704,45 @@ int launch_iteration(smle_csr_t a, const CgVecArgs &va, const CgScalars &cg)
     return rc;
 }
 
+// Batches of CG iterations with device-side convergence control.  `submit_batch()` queues `batch`
+// iterations (a graph launch, or that many kernel triples); batch j+1 is queued before the control
+// words of batch j are inspected, so the GPU never idles on the host round trip, and kernels queued
+// behind a raised STOP flag are no-ops.
+template <typename SubmitBatch>
+int run_cg_batches(CgWorkspace &w, int max_iters, int batch, SubmitBatch submit_batch)
+{
+    if (max_iters <= 0) return SMLE_OK;
+    cudaEvent_t ev[2];
+    CU(cudaEventCreateWithFlags(&ev[0], cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&ev[1], cudaEventDisableTiming));
+    auto submit = [&](int slot) -> int {
+        int r2 = submit_batch();
+        if (r2) return r2;
+        CU(cudaMemcpyAsync(w.ctrl_host + slot * CTRL_WORDS, w.ctrl, sizeof(int) * CTRL_WORDS,
+                           cudaMemcpyDeviceToHost, g_stream));
+        CU(cudaEventRecord(ev[slot], g_stream));
+        return SMLE_OK;
+    };
+    int launched = 0, j = 0;
+    int rc = submit(0);
+    launched += batch;
+    while (!rc) {
+        const bool more = launched < max_iters;
+        if (more) {
+            rc = submit((j + 1) & 1);
+            launched += batch;
+            if (rc) break;
+        }
+        cudaError_t e = cudaEventSynchronize(ev[j & 1]);
+        if (e != cudaSuccess) { rc = fail(SMLE_ERR_CUDA, "cudaEventSynchronize failed: %s", cudaGetErrorString(e)); break; }
+        if (w.ctrl_host[(j & 1) * CTRL_WORDS + CTRL_STOP] || !more) break;
+        ++j;
+    }
+    cudaEventDestroy(ev[0]);
+    cudaEventDestroy(ev[1]);
+    return rc;
+}
+
 // Solve A X = B.  B is a device pointer; the iterate lives in the workspace (w.Xd) so that the
 // captured graph never depends on caller pointers; the result is copied to X_dev (device) or
 // X_host (host) at the end.  tol < 0 never converges (fixed-count runs).
@@ -745,46 +782,19 @@ int cg_solve_device(smle_csr_t a, const double *B, double *X_dev, double *X_host
         w.graph_iters = kGraphIters;
     }
 
-    // Batches of iterations.  Batch j+1 is queued before the control words of batch j are
-    // inspected, so the GPU never idles on the host round trip; after the stop flag is up the
-    // queued kernels are no-ops.
     const int batch = use_graph ? w.graph_iters : 4;
-    cudaEvent_t ev[2];
-    CU(cudaEventCreateWithFlags(&ev[0], cudaEventDisableTiming));
-    CU(cudaEventCreateWithFlags(&ev[1], cudaEventDisableTiming));
-    auto submit = [&](int slot) -> int {
+    rc = run_cg_batches(w, max_iters, batch, [&]() -> int {
         if (use_graph) {
             CU(cudaGraphLaunch(w.graph, g_stream));
             g_launches += 3LL * batch;
-        } else {
-            for (int i = 0; i < batch; ++i) {
-                int r2 = launch_iteration(a, va, cg);
-                if (r2) return r2;
-            }
+            return SMLE_OK;
         }
-        CU(cudaMemcpyAsync(w.ctrl_host + slot * CTRL_WORDS, w.ctrl, sizeof(int) * CTRL_WORDS,
-                           cudaMemcpyDeviceToHost, g_stream));
-        CU(cudaEventRecord(ev[slot], g_stream));
+        for (int i = 0; i < batch; ++i) {
+            int r2 = launch_iteration(a, va, cg);
+            if (r2) return r2;
+        }
         return SMLE_OK;
-    };
-    if (max_iters > 0) {
-        int launched = 0, j = 0;
-        rc = submit(0);
-        launched += batch;
-        while (!rc) {
-            const bool more = launched < max_iters;
-            if (more) {
-                rc = submit((j + 1) & 1);
-                launched += batch;
-                if (rc) break;
-            }
-            CU(cudaEventSynchronize(ev[j & 1]));
-            if (w.ctrl_host[(j & 1) * CTRL_WORDS + CTRL_STOP] || !more) break;
-            ++j;
-        }
-    }
-    cudaEventDestroy(ev[0]);
-    cudaEventDestroy(ev[1]);
+    });
     if (rc) return rc;
 
     // result + final state
@@ -1038,18 +1048,6 @@ int smle_cg_multi_f64(smle_csr_t a, const double *B, double *X, int k, int max_i
 int smle_cg_run_fixed_f64(smle_csr_t a, const double *B, double *X, int k, int iters)
 {
     return cg_solve(a, B, X, k, iters, -1.0, 1, nullptr, nullptr, 0, nullptr, nullptr);
-}
-
-// debug: per-phase cycle counters of the SpMV kernel (meaningful only in -DSMLE_TIMING builds)
-int smle_debug_timing(long long *out4, int reset)
-{
-    int rc = ensure_init();
-    if (rc) return rc;
-    if (!g_timing) { CU(cudaMalloc(&g_timing, 64)); CU(cudaMemset(g_timing, 0, 64)); }
-    CU(cudaStreamSynchronize(g_stream));
-    if (out4) CU(cudaMemcpy(out4, g_timing, 64, cudaMemcpyDeviceToHost));
-    if (reset) CU(cudaMemset(g_timing, 0, 64));
-    return SMLE_OK;
 }
 
 int smle_cg_profile_f64(smle_csr_t a, const double *B, double *X, int k, int iters, float *ms_per_kernel)
@@ -1320,41 +1318,19 @@ int smle_dist_cg_f64(smle_dist_t d, const double *b_local_dev, double *x_local_d
         if (e != cudaSuccess) return fail(SMLE_ERR_CUDA, "graph instantiate failed: %s", cudaGetErrorString(e));
     }
     const int batch = use_graph ? kGraphIters : 4;
-    cudaEvent_t ev[2];
-    CU(cudaEventCreateWithFlags(&ev[0], cudaEventDisableTiming));
-    CU(cudaEventCreateWithFlags(&ev[1], cudaEventDisableTiming));
-    auto submit = [&](int slot) -> int {
+    const long long per_iter = d->ctl.fused ? 3LL : 4LL;
+    rc = run_cg_batches(w, max_iters, batch, [&]() -> int {
         if (use_graph) {
             CU(cudaGraphLaunch(d->graph, g_stream));
-            g_launches += (d->ctl.fused ? 3LL : 4LL) * batch;
-        } else {
-            for (int i = 0; i < batch; ++i) {
-                int r2 = dist_launch_iteration(d, va, cg);
-                if (r2) return r2;
-            }
+            g_launches += per_iter * batch;
+            return SMLE_OK;
         }
-        CU(cudaMemcpyAsync(w.ctrl_host + slot * CTRL_WORDS, w.ctrl, sizeof(int) * CTRL_WORDS, cudaMemcpyDeviceToHost, g_stream));
-        CU(cudaEventRecord(ev[slot], g_stream));
+        for (int i = 0; i < batch; ++i) {
+            int r2 = dist_launch_iteration(d, va, cg);
+            if (r2) return r2;
+        }
         return SMLE_OK;
-    };
-    if (max_iters > 0) {
-        int launched = 0, j = 0;
-        rc = submit(0);
-        launched += batch;
-        while (!rc) {
-            const bool more = launched < max_iters;
-            if (more) {
-                rc = submit((j + 1) & 1);
-                launched += batch;
-                if (rc) break;
-            }
-            CU(cudaEventSynchronize(ev[j & 1]));
-            if (w.ctrl_host[(j & 1) * CTRL_WORDS + CTRL_STOP] || !more) break;
-            ++j;
-        }
-    }
-    cudaEventDestroy(ev[0]);
-    cudaEventDestroy(ev[1]);
+    });
     if (rc) return rc;
     CU(cudaMemcpyAsync(x_local_dev, w.Xd, sizeof(double) * (size_t)d->n_local, cudaMemcpyDeviceToDevice, g_stream));
     CU(cudaMemcpyAsync(w.ctrl_host, w.ctrl, sizeof(int) * CTRL_WORDS, cudaMemcpyDeviceToHost, g_stream));

@@ -105,7 +105,6 @@ struct SpmvArgs {
     V *dot_part;                       // [gridDim.x]  (DOT)
     V *fix_part;                       // [gridDim.x]  (DOT)
     unsigned int *ticket;
-    long long *timing;                 // debug counters (only read with -DSMLE_TIMING)
     int debug_flags;                   // 1: skip compute (stream-only ceiling of the TMA pipeline)
     const DistCtl *dist;               // row-partitioned CG: post the local p.Ap to every peer (else NULL)
 };
