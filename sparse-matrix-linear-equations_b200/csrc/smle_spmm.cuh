@@ -7,7 +7,7 @@
 // the leading part of the row it stops in, whose partial sum is a carry-out.
 //
 // B200 mapping:
-//   * persistent CTAs (all co-resident), a producer warp streaming column indices / values / row
+//   * persistent CTAs, a producer warp streaming column indices / values / row
 //     offsets of each tile through shared memory with cp.async.bulk + mbarriers (L2 evict-first:
 //     A is read once per product), consumer warps that never meet at a CTA-wide barrier;
 //   * tiles are dealt to CTAs ROUND-ROBIN in chunks of `chunk` consecutive tiles, so at any
@@ -16,9 +16,10 @@
 //     every dense row comes from DRAM once instead of once per stencil plane;
 //   * a WORKER of G lanes owns one row at a time and covers G*VEC = min(k, 32*VEC) columns with
 //     VEC-wide (128-bit) loads of the dense rows: every nonzero (broadcast from shared memory) is
-//     reused across all k right-hand sides, and all dense-row loads of a row chunk are issued
-//     before the first FMA.  Workers sit on W consecutive rows, so the near-diagonal gathers hit
-//     L1;
+//     reused across all k right-hand sides.  The loads of a pass are unconditional (what lies
+//     behind a row in the staged indices is always a valid column), which lets ptxas pipeline
+//     them: ~4 requests of 512 B in flight per warp at 64 registers, 30 warps per SM.  Workers sit
+//     on W consecutive rows, so the near-diagonal gathers hit L1 (kept at 192 KB);
 //   * carries without fix-up passes and without waiting: the two tiles that share a cut row meet
 //     in a global slot (one per tile and column).  Each swaps its part in with an atomic
 //     exchange; the slot holds a signalling-NaN bit pattern that no arithmetic result can have
@@ -217,6 +218,7 @@ spmm_rows_kernel(SpmmArgs<V> a, CgScalars cg)
 {
     using SM = SpmmSmem<V, TILE>;
     static_assert(UB <= 16, "over-read room behind the staged column indices");
+    static_assert(THREADS % 32 == 0 && THREADS % G == 0 && G <= 32, "workers tile the consumer warps");
     constexpr int NW = THREADS / 32;
     constexpr int EPV = SM::EPV;
     constexpr int W = THREADS / G;         // workers per CTA
@@ -226,7 +228,7 @@ spmm_rows_kernel(SpmmArgs<V> a, CgScalars cg)
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ uint64_t s_full[STAGES], s_empty[STAGES];
     // the reduction scratch of the DOT epilogue reuses the stage buffers (all tiles are consumed by
-    // then): static shared memory stays at a few bytes, so that 2 stages of 2016 items fit the 64 KB
+    // then): static shared memory stays at a few bytes, so that 2 stages of 1920 items fit the 64 KB
     // carve-out and L1 keeps 192 KB for the dense-row gathers
     static_assert(!DOT || (size_t)(NW * KB + THREADS + 32) * sizeof(V) <= SM::STAGE_BYTES * STAGES, "epilogue scratch");
     V(*s_wsum)[KB] = reinterpret_cast<V(*)[KB]>(smem_raw);
