@@ -116,6 +116,15 @@ int smle_spmm_f32(smle_csr_t a, const float *X, float *Y, int k, int is_device_p
  * final_rel_res (nullable): sqrt(r.r)/||b|| at exit (max over columns for multi). */
 int smle_cg_single_f64(smle_csr_t a, const double *b, double *x, int max_iters, double tol,
                        int is_device_ptr, int *iters_out, double *final_rel_res);
+/* smle_cg_single_batch_f64 replaces the solve loop of TestCGSolveSingle
+ * (work_2025/main/single_strategy.hpp:199-226): num_vectors systems, vector v = b_vectors[v*n ...]
+ * and x_solutions[v*n ...] (host memory), solved one after another exactly like
+ * smle_cg_single_f64.  The upload of b_{v+1} and the download of x_{v-1} run on a copy stream
+ * while system v is being solved.  iters_each (nullable, num_vectors ints) receives the
+ * per-vector counts, *iters_total (nullable) their sum -- what the reference reports. */
+int smle_cg_single_batch_f64(smle_csr_t a, const double *b_vectors, double *x_solutions,
+                             int num_vectors, int max_iters, double tol, int *iters_each,
+                             long long *iters_total);
 int smle_cg_multi_f64(smle_csr_t a, const double *B, double *X, int k, int max_iters,
                       double tol, int kernel, int is_device_ptr, int *iters_out,
                       double *max_err_hist, int hist_capacity, int *hist_len,

@@ -111,6 +111,8 @@ struct CgWorkspace {
     size_t nk = 0;
     double *R = nullptr, *P = nullptr, *AP = nullptr;   // n x k blocks
     double *Bd = nullptr;                               // staging of B for host-pointer calls
+    double *Bd2[2] = {nullptr, nullptr};                // batch solves: double-buffered uploads of b
+    double *Xs = nullptr;                               // batch solves: x on its way to the host
     double *Xd = nullptr;                               // the iterate (graphs bake this pointer)
     double *scal = nullptr;                             // 6*k doubles + last_rel + tol
     int *conv = nullptr;
@@ -153,6 +155,7 @@ void free_workspace(CgWorkspace &w)
 {
     if (w.graph) cudaGraphExecDestroy(w.graph);
     cudaFree(w.R); cudaFree(w.P); cudaFree(w.AP); cudaFree(w.Bd); cudaFree(w.Xd);
+    cudaFree(w.Bd2[0]); cudaFree(w.Bd2[1]); cudaFree(w.Xs);
     cudaFree(w.scal); cudaFree(w.conv); cudaFree(w.ctrl); cudaFree(w.hist); cudaFree(w.part);
     if (w.ctrl_host) cudaFreeHost(w.ctrl_host);
     w = CgWorkspace();
@@ -1035,6 +1038,59 @@ int smle_cg_single_f64(smle_csr_t a, const double *b, double *x, int max_iters, 
                        int *iters_out, double *final_rel_res)
 {
     return cg_solve(a, b, x, 1, max_iters, tol, dev, iters_out, nullptr, 0, nullptr, final_rel_res);
+}
+
+int smle_cg_single_batch_f64(smle_csr_t a, const double *b_vectors, double *x_solutions, int num_vectors,
+                             int max_iters, double tol, int *iters_each, long long *iters_total)
+{
+    if (!a || !b_vectors || !x_solutions || num_vectors < 0) return fail(SMLE_ERR_ARG, "smle_cg_single_batch: bad argument");
+    if (a->vbytes != 8) return fail(SMLE_ERR_ARG, "CG needs an fp64 handle (reference CG is <double,int>)");
+    if (a->m != a->n) return fail(SMLE_ERR_ARG, "CG needs a square matrix");
+    int rc = ensure_init();
+    if (!rc) rc = ensure_workspace(a, 1, 0);
+    if (rc) return rc;
+    CgWorkspace &w = a->ws;
+    const size_t n = (size_t)a->m, vb = sizeof(double) * (n ? n : 1);
+    for (int i = 0; i < 2; ++i)
+        if (!w.Bd2[i]) CU(cudaMalloc(&w.Bd2[i], vb));
+    if (!w.Xs) CU(cudaMalloc(&w.Xs, vb));
+    static cudaStream_t copy_stream = nullptr;
+    if (!copy_stream) CU(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
+    cudaEvent_t b_ready[2], x_ready, x_free;
+    for (auto *e : {&b_ready[0], &b_ready[1], &x_ready, &x_free}) CU(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+
+    long long total = 0;
+    rc = SMLE_OK;
+    if (num_vectors > 0) {
+        CU(cudaMemcpyAsync(w.Bd2[0], b_vectors, sizeof(double) * n, cudaMemcpyHostToDevice, copy_stream));
+        CU(cudaEventRecord(b_ready[0], copy_stream));
+    }
+    for (int v = 0; v < num_vectors && !rc; ++v) {
+        // b_v is on the device when the solve starts; b_{v+1} follows on the copy stream meanwhile (its
+        // buffer was last read by solve v-1, which this thread has already waited for)
+        CU(cudaStreamWaitEvent(g_stream, b_ready[v & 1], 0));
+        if (v + 1 < num_vectors) {
+            CU(cudaMemcpyAsync(w.Bd2[(v + 1) & 1], b_vectors + (size_t)(v + 1) * n, sizeof(double) * n,
+                               cudaMemcpyHostToDevice, copy_stream));
+            CU(cudaEventRecord(b_ready[(v + 1) & 1], copy_stream));
+        }
+        if (v > 0) CU(cudaStreamWaitEvent(g_stream, x_free, 0));   // x_{v-1} has left the staging buffer
+        int iters = 0;
+        rc = cg_solve_device(a, w.Bd2[v & 1], w.Xs, nullptr, 1, max_iters, tol, &iters, nullptr, 0, nullptr, nullptr);
+        if (rc) break;
+        // x_v travels to the host while system v+1 is being solved
+        CU(cudaEventRecord(x_ready, g_stream));
+        CU(cudaStreamWaitEvent(copy_stream, x_ready, 0));
+        CU(cudaMemcpyAsync(x_solutions + (size_t)v * n, w.Xs, sizeof(double) * n, cudaMemcpyDeviceToHost, copy_stream));
+        CU(cudaEventRecord(x_free, copy_stream));
+        if (iters_each) iters_each[v] = iters;
+        total += iters;
+    }
+    cudaError_t e = cudaStreamSynchronize(copy_stream);
+    if (!rc && e != cudaSuccess) rc = fail(SMLE_ERR_CUDA, "copy stream failed: %s", cudaGetErrorString(e));
+    for (auto ev : {b_ready[0], b_ready[1], x_ready, x_free}) cudaEventDestroy(ev);
+    if (iters_total) *iters_total = total;
+    return rc;
 }
 
 int smle_cg_multi_f64(smle_csr_t a, const double *B, double *X, int k, int max_iters, double tol, int kernel,

@@ -235,6 +235,21 @@ class CsrMatrix:
                                         C.byref(it), C.byref(rel)))
         return it.value, x, rel.value
 
+    def cg_solve_single_batch(self, b_vectors, max_iters: int, tolerance: float, out=None):
+        """-> (iterations per vector, X)   the solve loop of TestCGSolveSingle (single_strategy.hpp:199-226):
+        b_vectors is an (L, n) HOST array (numpy or pinned torch), vector v = row v; the host copies of
+        neighbouring systems overlap with the solves."""
+        pb, dev, _ = _arg(b_vectors, np.float64)
+        L = int(b_vectors.shape[0])
+        x = out if out is not None else _empty_like_arg(b_vectors, (L, self.num_rows), np.float64)
+        px, dev_x, _ = _arg(x, np.float64, writable=True)
+        if dev or dev_x:
+            raise SmleError("cg_solve_single_batch takes host memory (device callers use cg_solve_single)")
+        each = (C.c_int * max(L, 1))()
+        total = C.c_longlong(0)
+        _check(lib().smle_cg_single_batch_f64(self._h, pb, px, _I(L), _I(max_iters), _D(tolerance), each, C.byref(total)))
+        return [each[i] for i in range(L)], x
+
     def cg_solve_multiple(self, B, max_iters: int, tolerance: float, kernel_type: int = MERGE,
                           out=None, want_history: bool = True):
         """-> (iterations, X, max_errors, final_rel_res)

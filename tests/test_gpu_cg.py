@@ -115,3 +115,24 @@ def test_cg_at_baseline_size_converges(gpu):
     true_rel = (r.norm() / b.norm()).item()
     assert 0 < it < 2000 and rel < 1e-8 and true_rel < 2e-8, (it, rel, true_rel)
     a.close()
+
+
+def test_single_batch_matches_one_by_one(gpu, orc):
+    """smle_cg_single_batch_f64 (the solve loop of TestCGSolveSingle with overlapped host copies) gives
+    exactly the iterates of L separate smle_cg_single_f64 calls."""
+    ro, ci, va = gpu.gen_grid3d(30, True, 6.0, -1.0)
+    n = len(ro) - 1
+    a = gpu.CsrMatrix(ro, ci, va)
+    L = 5
+    B = gpu.gen_rhs_rand(42, n * L).reshape(L, n).copy()
+    its, X = a.cg_solve_single_batch(B, 10000, 1e-7)
+    for v in range(L):
+        it1, x1, _ = a.cg_solve_single(B[v], 10000, 1e-7)
+        assert it1 == its[v]
+        assert np.array_equal(x1, X[v]), v
+    it_ref, x_ref = orc.cg_single(ro, ci, va, B[L - 1], 10000, 1e-7)
+    assert abs(its[-1] - it_ref) <= max(1, round(0.02 * it_ref))
+    assert np.abs(X[-1] - x_ref).max() <= 1e-6 * np.abs(x_ref).max()
+    its0, _ = a.cg_solve_single_batch(B[:0], 10, 1e-7)
+    assert its0 == []
+    a.close()
