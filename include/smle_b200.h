@@ -66,6 +66,13 @@ int smle_malloc(void **dev_ptr, unsigned long long bytes);
 int smle_free(void *dev_ptr);
 int smle_copy_to_device(void *dev_dst, const void *host_src, unsigned long long bytes);
 int smle_copy_to_host(void *host_dst, const void *dev_src, unsigned long long bytes);
+/* Page-lock caller-owned host memory for the duration of a series of calls (cudaHostRegister): with
+ * pageable buffers the runtime stages every copy and the batch solve below cannot overlap copies
+ * with solves.  The adapters register the driver's b / x blocks once, outside the timing loop
+ * (the reference allocates them with mkl_malloc, cpu_singlecg.cpp:80-86).  Already-pinned memory is
+ * accepted as is. */
+int smle_host_register(void *host_ptr, unsigned long long bytes);
+int smle_host_unregister(void *host_ptr);
 
 /* ---- merge-path partition -----------------------------------------------------------
  * Replaces MergePathSearch (work_2025/spmm/merge_based.hpp:22-44; copies at
@@ -143,25 +150,55 @@ int smle_cg_profile_f64(smle_csr_t a, const double *B, double *X, int k, int ite
  * Net-new relative to the reference (which has no distributed code); semantics of the solve are
  * CGSolveSingle's (single_strategy.hpp:105-170) on the global system.  The partition is cut at
  * the reference's merge-path coordinates: part g owns rows [x_g, x_{g+1}) with
- * x_g = MergePathSearch(min(g*ceil((m+nnz)/G), m+nnz)).x (smle_merge_path_partition).
- *   local_a      this rank's rows; columns remapped to [0,n_local) own | [n_local,n_local+n_halo) halo
- *   send_off     world+1 offsets into send_idx: entries this rank pushes to each peer
- *   send_idx     local row indices of those entries (grouped by peer, in the peer's halo order)
- *   send_dst     per peer: element offset in THAT peer's extended vector where the group lands
- *   needs_from   per peer: 1 when this rank receives halo entries from it
+ * x_g = MergePathSearch(min(g*ceil((m+nnz)/G), m+nnz)).x (merge_based.hpp:22-44 on the share
+ * diagonals :72-82); a row cut mid-way belongs whole to the later part.
+ *
+ * smle_dist_bounds   bounds[world+1] from the GLOBAL row offsets (m+1 host ints; the search runs on
+ *                    the GPU like smle_merge_path_partition and is bit-exact with the reference).
+ *                    Only the row offsets are global -- no rank needs the whole matrix.
+ *
+ * Planner (host only, csrc/smle_plan.cpp).  A rank hands in ITS rows only:
+ *   smle_dist_plan_create      rows [bounds[rank], bounds[rank+1]) as local row offsets (starting
+ *                              at 0) + GLOBAL column indices.  Builds the halo index map (sorted
+ *                              unique out-of-range columns) and the local column indices
+ *                              [0,n_local) own | pad | [halo_base, halo_base+n_halo) halo, halo_base
+ *                              = n_local rounded up to a 128-byte line.
+ *   smle_dist_plan_request     the int blob this rank publishes (size: _request_size ints).
+ *   smle_dist_plan_finish      all ranks' blobs, concatenated in rank order (blob_off[world+1] int
+ *                              offsets), turn into the push plan: which local rows go to which peer
+ *                              and where they land in that peer's extended vector.  The caller moves
+ *                              the blobs (torch.distributed all-gather, shared memory, MPI ...).
+ *   smle_dist_plan_send        the push plan, for inspection: send_off[world+1], send_idx
+ *                              [send_off[world]], send_dst[world], needs_from[world] (each nullable).
+ *   smle_dist_create_from_plan uploads the local system (values = the rank's rows, in CSR order)
+ *                              and allocates the communication buffer.
  * smle_dist_ipc_handle / smle_dist_connect exchange the 64-byte CUDA IPC handles of the per-rank
- * communication buffers (the caller moves the bytes, e.g. torch.distributed.all_gather).
- * smle_dist_spmv_f64 and smle_dist_cg_f64 are collective over the partition; vectors are device
- * pointers to this rank's rows.  Halo pushes and the dot-product all-reduce are done by the
- * kernels themselves through peer stores and mailbox flags -- no NCCL on the data path. */
+ * communication buffers (again moved by the caller; world == 1 passes NULL).
+ * smle_dist_spmv_f64 and smle_dist_cg_f64 are collective over the partition; vectors hold this
+ * rank's rows (smle_dist_spmv_f64: device pointers; smle_dist_cg_f64: device or host memory per
+ * is_device_ptr).  Halo pushes and the dot-product all-reduce are done by the kernels themselves
+ * through peer stores and mailbox flags -- no NCCL on the data path.  A peer that stays silent for
+ * 4 s makes every rank return SMLE_ERR_COMM instead of hanging. */
 typedef struct smle_dist_s *smle_dist_t;
-int smle_dist_create(smle_dist_t *out, smle_csr_t local_a, int rank, int world, int n_local, int n_halo,
-                     const int *send_off, const int *send_idx, const int *send_dst, const int *needs_from);
+typedef struct smle_plan_s *smle_plan_t;
+int smle_dist_bounds(const int *row_offsets, int m, int world, int *bounds);
+int smle_dist_plan_create(smle_plan_t *out, int rank, int world, const int *bounds, int num_cols_global,
+                          const int *local_row_offsets, const int *global_column_indices);
+int smle_dist_plan_dims(smle_plan_t p, int *n_local, int *n_halo, int *halo_base, int *nnz_local);
+int smle_dist_plan_local_columns(smle_plan_t p, int *out);
+int smle_dist_plan_halo_columns(smle_plan_t p, int *out);
+long long smle_dist_plan_request_size(smle_plan_t p);
+int smle_dist_plan_request(smle_plan_t p, int *blob);
+int smle_dist_plan_finish(smle_plan_t p, const int *all_blobs, const long long *blob_off);
+int smle_dist_plan_send(smle_plan_t p, int *send_off, int *send_idx, int *send_dst, int *needs_from);
+void smle_dist_plan_destroy(smle_plan_t p);
+int smle_dist_create_from_plan(smle_dist_t *out, smle_plan_t p, const double *local_values);
 int smle_dist_ipc_handle(smle_dist_t d, unsigned char *out64);
 int smle_dist_connect(smle_dist_t d, const unsigned char *all_handles);
+int smle_dist_dims(smle_dist_t d, int *n_local, int *n_halo, int *rank, int *world);
 int smle_dist_spmv_f64(smle_dist_t d, const double *x_local_dev, double *y_local_dev);
-int smle_dist_cg_f64(smle_dist_t d, const double *b_local_dev, double *x_local_dev, int max_iters, double tol,
-                     int *iters_out, double *final_rel_res);
+int smle_dist_cg_f64(smle_dist_t d, const double *b_local, double *x_local, int max_iters, double tol,
+                     int is_device_ptr, int *iters_out, double *final_rel_res);
 void smle_dist_destroy(smle_dist_t d);
 
 /* ---- matrix / RHS generators (host side) -------------------------------------------------
@@ -183,6 +220,12 @@ int smle_gen_grid3d_f64(int width, int self_loop, double diag, double offd, int 
                         int *column_indices, double *values);
 int smle_gen_grid3d_f32(int width, int self_loop, float diag, float offd, int *row_offsets,
                         int *column_indices, float *values);
+/* Slab-local generation for the row-partitioned solve: the global row offsets alone
+ * (m+1 ints), and rows [r0, r1) of the same matrix -- local_row_offsets[r1-r0+1] starting at 0,
+ * GLOBAL column indices and values, row_offsets[r1]-row_offsets[r0] of each. */
+int smle_gen_grid3d_row_offsets(int width, int self_loop, int *row_offsets);
+int smle_gen_grid3d_rows_f64(int width, int self_loop, double diag, double offd, int r0, int r1,
+                             int *local_row_offsets, int *column_indices, double *values);
 int smle_gen_wheel_f64(int spokes, double value, int *row_offsets, int *column_indices,
                        double *values);
 int smle_gen_wheel_f32(int spokes, float value, int *row_offsets, int *column_indices,
@@ -203,6 +246,9 @@ int smle_gen_rmat_f32(int scale, int edge_factor, double a, double b, double c,
 /* RHS as the CG drivers build it: srand(seed); b[i] = rand()/RAND_MAX, i < count
  * (cpu_singlecg.cpp:88-90, cpu_multicg.cpp:164-166); glibc rand(). */
 int smle_gen_rhs_rand_f64(unsigned seed, long long count, double *out);
+/* entries [first, first+count) of the same stream (the generator is sequential: `first` values are
+ * drawn and dropped), for a rank that holds only its rows of b */
+int smle_gen_rhs_rand_range_f64(unsigned seed, long long first, long long count, double *out);
 /* the drivers' tolerance quirk: ||b[0:n]||_2 * tol (cpu_singlecg.cpp:23-34, cpu_multicg.cpp:50-62) */
 double smle_driver_threshold_f64(const double *b, int n, double tol);
 

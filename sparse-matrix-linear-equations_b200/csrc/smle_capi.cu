@@ -21,6 +21,7 @@
 #include "smle_spmv.cuh"
 #include "smle_spmm.cuh"
 #include "smle_dist.cuh"
+#include "smle_plan.h"
 
 using namespace smle;
 
@@ -32,6 +33,7 @@ namespace {
 thread_local char g_err[512] = "";
 cudaStream_t g_own_stream = nullptr;   // created by smle_init
 cudaStream_t g_stream = nullptr;       // the stream in use (own or caller's)
+cudaStream_t g_copy_stream = nullptr;  // host <-> device copies that overlap a solve (batch solves)
 int g_device = -1;
 int g_sms = 0;
 long long g_launches = 0;
@@ -60,9 +62,13 @@ int ensure_init()
     return smle_init(0);
 }
 
+cudaError_t g_launch_err = cudaSuccess;   // first failure of cudaLaunchKernelEx since the last check_launch()
+
 int check_launch(const char *what)
 {
     cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = g_launch_err;
+    g_launch_err = cudaSuccess;
     if (e != cudaSuccess) return fail(SMLE_ERR_CUDA, "launch of %s failed: %s", what, cudaGetErrorString(e));
     return SMLE_OK;
 }
@@ -92,7 +98,8 @@ void launch_kernel(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, A
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = g_pdl ? 1 : 0;
-    cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);   // errors surface through check_launch()
+    const cudaError_t e = cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+    if (e != cudaSuccess && g_launch_err == cudaSuccess) g_launch_err = e;   // reported by check_launch()
 }
 
 struct PdlScope {   // CG iteration launches inside this scope use PDL
@@ -123,6 +130,7 @@ struct CgWorkspace {
     int *ctrl_host = nullptr;                           // pinned mirror of ctrl
     cudaGraphExec_t graph = nullptr;                    // `graph_iters` iterations of K1,K2,K3
     int graph_iters = 0;
+    unsigned graph_epoch = 0;                           // scratch_epoch of the handle when the graph was captured
 };
 
 struct Partition {
@@ -131,6 +139,7 @@ struct Partition {
     int2 *xy = nullptr;   // device, num_tiles + 1
     int *maxlen = nullptr; // device, num_tiles: longest in-tile row segment
     int max_len = 0;       // max over maxlen[] (host copy): picks the SpMM kernel
+    unsigned char *halo = nullptr;   // device, num_tiles: tile gathers halo columns (row-partitioned handles only)
 };
 
 struct smle_csr_s {
@@ -146,6 +155,11 @@ struct smle_csr_s {
     unsigned int *ticket = nullptr;
     void *tile_carry = nullptr;       // carry slots of spmm_rows_kernel (sentinel-filled)
     size_t tile_carry_elems = 0;
+    void *cta_slot = nullptr;         // carry slots of the CTA boundaries of spmv_kernel (sentinel-filled)
+    // Captured CUDA graphs bake the scratch pointers above: every reallocation bumps the epoch and
+    // graphs captured under an older epoch are rebuilt before their next launch.
+    unsigned scratch_epoch = 0;
+    int halo_base = -1;               // local block of a row partition: first halo column (else -1)
     CgWorkspace ws;
 };
 
@@ -195,6 +209,13 @@ int get_partition(smle_csr_t a, int items_per_tile, Partition **out)
         CU(cudaStreamSynchronize(g_stream));
         cudaFree(d_max);
     }
+    if (a->halo_base >= 0) {
+        CU(cudaMalloc(&p.halo, (size_t)p.num_tiles));
+        tile_halo_kernel<<<(p.num_tiles * 32 + 255) / 256, 256, 0, g_stream>>>(a->ci, p.xy, p.num_tiles, a->halo_base, p.halo);
+        ++g_launches;
+        rc = check_launch("tile_halo_kernel");
+        if (rc) return rc;
+    }
     a->parts[items_per_tile] = p;
     *out = &a->parts[items_per_tile];
     return SMLE_OK;
@@ -207,8 +228,16 @@ int ensure_scratch(smle_csr_t a, int k)
         CU(cudaMalloc(&a->carry_row, sizeof(int) * (size_t)a->max_ctas));
         CU(cudaMalloc(&a->ticket, sizeof(unsigned int) * 4));
         CU(cudaMemsetAsync(a->ticket, 0, sizeof(unsigned int) * 4, g_stream));
+        CU(cudaMalloc(&a->cta_slot, 8 * (size_t)a->max_ctas));
+        if (a->vbytes == 8) smle::fill_sentinel_kernel<double><<<4, 256, 0, g_stream>>>((double *)a->cta_slot, (size_t)a->max_ctas);
+        else smle::fill_sentinel_kernel<float><<<4, 256, 0, g_stream>>>((float *)a->cta_slot, (size_t)a->max_ctas);
+        ++g_launches;
+        int rc = check_launch("fill_sentinel_kernel");
+        if (rc) return rc;
     }
     if (k > a->carry_k) {
+        if (g_stream) cudaStreamSynchronize(g_stream);   // nothing in flight may still use the old buffers
+        ++a->scratch_epoch;
         cudaFree(a->carry_val); cudaFree(a->dot_part); cudaFree(a->fix_part);
         a->carry_val = a->dot_part = a->fix_part = nullptr;
         size_t bytes = (size_t)a->max_ctas * (size_t)k * 8;
@@ -293,6 +322,8 @@ template <typename V>
 int ensure_tile_carry(smle_csr_t a, size_t elems)
 {
     if (elems <= a->tile_carry_elems) return SMLE_OK;
+    if (g_stream) cudaStreamSynchronize(g_stream);
+    ++a->scratch_epoch;
     cudaFree(a->tile_carry);
     a->tile_carry = nullptr; a->tile_carry_elems = 0;
     CU(cudaMalloc(&a->tile_carry, sizeof(V) * elems));
@@ -477,10 +508,11 @@ int launch_spmv_t(smle_csr_t a, const V *x, V *y, const CgScalars &cg, bool dry)
     args.x = x; args.y = y; args.tile_xy = p->xy; args.tile_maxlen = p->maxlen;
     args.m = a->m; args.nnz = a->nnz;
     args.num_tiles = p->num_tiles; args.tiles_per_cta = tiles_per_cta;
-    args.carry_row = a->carry_row; args.carry_val = (V *)a->carry_val;
-    args.dot_part = (V *)a->dot_part; args.fix_part = (V *)a->fix_part;
+    args.cta_slot = (V *)a->cta_slot;
+    args.dot_part = (V *)a->dot_part;
     args.ticket = a->ticket;
     args.dist = (const DistCtl *)g_spmv_dist;
+    args.tile_halo = g_spmv_dist ? p->halo : nullptr;
     { static int dbg = -1; if (dbg < 0) { const char *e = getenv("SMLE_SPMV_DEBUG"); dbg = e ? atoi(e) : 0; } args.debug_flags = dbg; }
     launch_kernel(kern, dim3(grid), dim3(THREADS + 32), smem, args, cg);   // + the producer warp
     ++g_launches;
@@ -768,8 +800,12 @@ int cg_solve_device(smle_csr_t a, const double *B, double *X_dev, double *X_host
     if (rc) return rc;
 
     const bool use_graph = getenv("SMLE_NO_GRAPH") == nullptr;
+    if (w.graph && w.graph_epoch != a->scratch_epoch) {   // scratch was reallocated since the capture
+        cudaGraphExecDestroy(w.graph);
+        w.graph = nullptr;
+    }
     if (use_graph && !w.graph) {
-        // lazy setup (partition kernel, occupancy query) must happen outside the capture
+        // lazy setup (partition kernel, occupancy query, scratch growth) must happen outside the capture
         rc = launch_merge<double, true>(a, va.P, va.AP, k, cg, /*dry=*/true);
         if (rc) return rc;
         cudaGraph_t graph;
@@ -783,6 +819,7 @@ int cg_solve_device(smle_csr_t a, const double *B, double *X_dev, double *X_host
         cudaGraphDestroy(graph);
         if (e != cudaSuccess) return fail(SMLE_ERR_CUDA, "graph instantiate failed: %s", cudaGetErrorString(e));
         w.graph_iters = kGraphIters;
+        w.graph_epoch = a->scratch_epoch;
     }
 
     const int batch = use_graph ? w.graph_iters : 4;
@@ -863,23 +900,51 @@ int smle_init(int device)
     int n = smle_device_count();
     if (n < 1) return fail(SMLE_ERR_CUDA, "no CUDA device: this library has no CPU fallback");
     if (device < 0 || device >= n) return fail(SMLE_ERR_ARG, "device %d out of range (%d visible)", device, n);
+    if (g_device == device) {   // already bound: keep the stream (cached CUDA graphs were captured on it)
+        CU(cudaSetDevice(device));
+        return SMLE_OK;
+    }
+    if (g_device >= 0)
+        return fail(SMLE_ERR_ARG, "this process is bound to device %d (one process drives one GPU); "
+                                  "destroy the handles and call smle_shutdown() before binding to device %d", g_device, device);
     CU(cudaSetDevice(device));
     cudaDeviceProp prop;
     CU(cudaGetDeviceProperties(&prop, device));
     g_sms = prop.multiProcessorCount;
     const bool using_own = (g_stream == g_own_stream);
-    if (g_own_stream) cudaStreamDestroy(g_own_stream);
     CU(cudaStreamCreateWithFlags(&g_own_stream, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&g_copy_stream, cudaStreamNonBlocking));
     g_device = device;
     if (using_own) g_stream = g_own_stream;
     return SMLE_OK;
 }
 
+/* Handles must be destroyed first: they own CUDA graphs captured on the library's stream. */
 void smle_shutdown(void)
 {
-    if (g_own_stream) cudaStreamDestroy(g_own_stream);
-    g_own_stream = g_stream = nullptr;
+    if (g_own_stream) { cudaStreamSynchronize(g_own_stream); cudaStreamDestroy(g_own_stream); }
+    if (g_copy_stream) { cudaStreamSynchronize(g_copy_stream); cudaStreamDestroy(g_copy_stream); }
+    g_own_stream = g_stream = g_copy_stream = nullptr;
     g_device = -1;
+}
+
+int smle_host_register(void *host_ptr, unsigned long long bytes)
+{
+    int rc = ensure_init();
+    if (rc) return rc;
+    if (!host_ptr || !bytes) return SMLE_OK;
+    cudaError_t e = cudaHostRegister(host_ptr, bytes, cudaHostRegisterDefault);
+    if (e == cudaErrorHostMemoryAlreadyRegistered) { cudaGetLastError(); return SMLE_OK; }
+    if (e != cudaSuccess) { cudaGetLastError(); return fail(SMLE_ERR_CUDA, "cudaHostRegister(%llu bytes) failed: %s", bytes, cudaGetErrorString(e)); }
+    return SMLE_OK;
+}
+
+int smle_host_unregister(void *host_ptr)
+{
+    if (!host_ptr) return SMLE_OK;
+    cudaError_t e = cudaHostUnregister(host_ptr);
+    if (e != cudaSuccess) { cudaGetLastError(); return fail(SMLE_ERR_CUDA, "cudaHostUnregister failed: %s", cudaGetErrorString(e)); }
+    return SMLE_OK;
 }
 
 int smle_set_stream(void *s)
@@ -985,10 +1050,10 @@ void smle_csr_destroy(smle_csr_t a)
     if (!a) return;
     if (g_stream) cudaStreamSynchronize(g_stream);
     free_workspace(a->ws);
-    for (auto &kv : a->parts) { cudaFree(kv.second.xy); cudaFree(kv.second.maxlen); }
+    for (auto &kv : a->parts) { cudaFree(kv.second.xy); cudaFree(kv.second.maxlen); cudaFree(kv.second.halo); }
     cudaFree(a->ro); cudaFree(a->ci); cudaFree(a->va);
     cudaFree(a->carry_row); cudaFree(a->carry_val); cudaFree(a->dot_part); cudaFree(a->fix_part);
-    cudaFree(a->ticket); cudaFree(a->tile_carry);
+    cudaFree(a->ticket); cudaFree(a->tile_carry); cudaFree(a->cta_slot);
     delete a;
 }
 
@@ -1054,18 +1119,18 @@ int smle_cg_single_batch_f64(smle_csr_t a, const double *b_vectors, double *x_so
     for (int i = 0; i < 2; ++i)
         if (!w.Bd2[i]) CU(cudaMalloc(&w.Bd2[i], vb));
     if (!w.Xs) CU(cudaMalloc(&w.Xs, vb));
-    static cudaStream_t copy_stream = nullptr;
-    if (!copy_stream) CU(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
-    cudaEvent_t b_ready[2], x_ready, x_free;
-    for (auto *e : {&b_ready[0], &b_ready[1], &x_ready, &x_free}) CU(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+    cudaStream_t copy_stream = g_copy_stream;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};   // b_ready[0], b_ready[1], x_ready, x_free
+    for (auto &e : ev)
+        if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) {
+            for (auto e2 : ev) if (e2) cudaEventDestroy(e2);
+            return fail(SMLE_ERR_CUDA, "cudaEventCreate failed");
+        }
+    cudaEvent_t *b_ready = ev, x_ready = ev[2], x_free = ev[3];
 
     long long total = 0;
-    rc = SMLE_OK;
-    if (num_vectors > 0) {
-        CU(cudaMemcpyAsync(w.Bd2[0], b_vectors, sizeof(double) * n, cudaMemcpyHostToDevice, copy_stream));
-        CU(cudaEventRecord(b_ready[0], copy_stream));
-    }
-    for (int v = 0; v < num_vectors && !rc; ++v) {
+    // the loop body returns through `step`, so the events are destroyed on every path
+    auto step = [&](int v) -> int {
         // b_v is on the device when the solve starts; b_{v+1} follows on the copy stream meanwhile (its
         // buffer was last read by solve v-1, which this thread has already waited for)
         CU(cudaStreamWaitEvent(g_stream, b_ready[v & 1], 0));
@@ -1076,8 +1141,8 @@ int smle_cg_single_batch_f64(smle_csr_t a, const double *b_vectors, double *x_so
         }
         if (v > 0) CU(cudaStreamWaitEvent(g_stream, x_free, 0));   // x_{v-1} has left the staging buffer
         int iters = 0;
-        rc = cg_solve_device(a, w.Bd2[v & 1], w.Xs, nullptr, 1, max_iters, tol, &iters, nullptr, 0, nullptr, nullptr);
-        if (rc) break;
+        int r2 = cg_solve_device(a, w.Bd2[v & 1], w.Xs, nullptr, 1, max_iters, tol, &iters, nullptr, 0, nullptr, nullptr);
+        if (r2) return r2;
         // x_v travels to the host while system v+1 is being solved
         CU(cudaEventRecord(x_ready, g_stream));
         CU(cudaStreamWaitEvent(copy_stream, x_ready, 0));
@@ -1085,10 +1150,18 @@ int smle_cg_single_batch_f64(smle_csr_t a, const double *b_vectors, double *x_so
         CU(cudaEventRecord(x_free, copy_stream));
         if (iters_each) iters_each[v] = iters;
         total += iters;
+        return SMLE_OK;
+    };
+    rc = SMLE_OK;
+    if (num_vectors > 0) {
+        cudaError_t e0 = cudaMemcpyAsync(w.Bd2[0], b_vectors, sizeof(double) * n, cudaMemcpyHostToDevice, copy_stream);
+        if (e0 == cudaSuccess) e0 = cudaEventRecord(b_ready[0], copy_stream);
+        if (e0 != cudaSuccess) rc = fail(SMLE_ERR_CUDA, "upload of b failed: %s", cudaGetErrorString(e0));
     }
+    for (int v = 0; v < num_vectors && !rc; ++v) rc = step(v);
     cudaError_t e = cudaStreamSynchronize(copy_stream);
     if (!rc && e != cudaSuccess) rc = fail(SMLE_ERR_CUDA, "copy stream failed: %s", cudaGetErrorString(e));
-    for (auto ev : {b_ready[0], b_ready[1], x_ready, x_free}) cudaEventDestroy(ev);
+    for (auto e2 : ev) cudaEventDestroy(e2);
     if (iters_total) *iters_total = total;
     return rc;
 }
@@ -1155,20 +1228,22 @@ int smle_cg_profile_f64(smle_csr_t a, const double *B, double *X, int k, int ite
 } // extern "C"
 
 // =========================================================================================
-// row-partitioned CG over NVLink peer memory (one process per GPU; smle_dist.cuh)
+// row-partitioned CG over NVLink peer memory (one process per GPU; smle_dist.cuh, smle_plan.cpp)
 // =========================================================================================
 struct smle_dist_s {
-    smle_csr_t a = nullptr;            // local rows, columns remapped to [own | halo]
-    int rank = 0, world = 1, n_local = 0, n_halo = 0;
-    unsigned char *comm = nullptr;     // [DistBlock (4 KB) | p vector (n_local + n_halo doubles)]
+    smle_csr_t a = nullptr;            // local rows, columns remapped to [own | pad | halo] (owned)
+    int rank = 0, world = 1, n_local = 0, n_halo = 0, halo_base = 0;
+    unsigned char *comm = nullptr;     // [DistBlock (4 KB) | p vector (halo_base + n_halo doubles)]
     void *peer_base[kMaxRanks] = {};
     int *send_idx = nullptr;
     unsigned int *ticket = nullptr;
     DistCtl ctl;
-    DistCtl *ctl_dev = nullptr;        // device copy (read by the SpMV kernel's epilogue)
+    DistCtl *ctl_dev = nullptr;        // device copy (read by the SpMV kernel)
     int seq_base = 0;
     cudaGraphExec_t graph = nullptr;
+    unsigned graph_epoch = 0;
     bool connected = false;
+    double *b_stage = nullptr, *x_stage = nullptr;   // host-pointer calls
 };
 
 namespace {
@@ -1192,8 +1267,9 @@ int dist_push_grid(smle_dist_t d)
 
 int dist_launch_iteration(smle_dist_t d, const CgVecArgs &va, const CgScalars &cg)
 {
-    // K1 local SpMV + p.Ap posted to the peers | K2 all-reduce -> alpha, r update, r.r posted |
-    // K3 all-reduce -> beta, x/p update, iteration state | halo push + sequence numbers
+    // K1 local SpMV (boundary tiles wait for the halo) + p.Ap posted to the peers |
+    // K2 all-reduce -> alpha, r update, r.r posted |
+    // K3 all-reduce -> beta, x/p update + halo push, iteration state | [separate halo push kernel]
     g_spmv_dist = d->ctl_dev;
     int rc = launch_merge<double, true>(d->a, va.P, va.AP, 1, cg);
     g_spmv_dist = nullptr;
@@ -1206,24 +1282,15 @@ int dist_launch_iteration(smle_dist_t d, const CgVecArgs &va, const CgScalars &c
     return check_launch("distributed CG iteration");
 }
 
-} // namespace
-
-extern "C" {
-
-int smle_dist_create(smle_dist_t *out, smle_csr_t local_a, int rank, int world, int n_local, int n_halo,
-                     const int *send_off, const int *send_idx, const int *send_dst, const int *needs_from)
+int dist_create(smle_dist_t *out, smle_csr_t local_a, int rank, int world, int n_local, int n_halo, int halo_base,
+                const int *send_off, const int *send_idx, const int *send_dst, const int *needs_from)
 {
-    if (!out || !local_a || world < 1 || world > kMaxRanks || rank < 0 || rank >= world || n_local < 0 || n_halo < 0 ||
-        !send_off || !send_dst || !needs_from)
-        return fail(SMLE_ERR_ARG, "smle_dist_create: bad argument (world must be 1..%d)", kMaxRanks);
-    if (local_a->vbytes != 8 || local_a->m != n_local || local_a->n != n_local + n_halo)
-        return fail(SMLE_ERR_ARG, "local matrix must be fp64 with n_local rows and n_local+n_halo columns");
-    int rc = ensure_init();
-    if (rc) return rc;
     smle_dist_s *d = new (std::nothrow) smle_dist_s();
     if (!d) return fail(SMLE_ERR_ALLOC, "out of host memory");
-    d->a = local_a; d->rank = rank; d->world = world; d->n_local = n_local; d->n_halo = n_halo;
-    size_t bytes = kDistCtlBytes + sizeof(double) * ((size_t)n_local + n_halo + 2);
+    *out = d;   // the caller destroys it on failure
+    d->a = local_a; d->rank = rank; d->world = world; d->n_local = n_local; d->n_halo = n_halo; d->halo_base = halo_base;
+    local_a->halo_base = halo_base;   // partitions of this handle flag the tiles that gather halo columns
+    size_t bytes = kDistCtlBytes + sizeof(double) * ((size_t)halo_base + n_halo + 2);
     CU(cudaMalloc(&d->comm, bytes));
     CU(cudaMemsetAsync(d->comm, 0, bytes, g_stream));
     int total = send_off[world];
@@ -1232,6 +1299,8 @@ int smle_dist_create(smle_dist_t *out, smle_csr_t local_a, int rank, int world, 
     CU(cudaMalloc(&d->ticket, sizeof(unsigned int) * 4));
     CU(cudaMemsetAsync(d->ticket, 0, sizeof(unsigned int) * 4, g_stream));
     CU(cudaStreamSynchronize(g_stream));
+    int rc = ensure_workspace(local_a, 1, 0);
+    if (rc) return rc;
     DistCtl &c = d->ctl;
     memset(&c, 0, sizeof(c));
     c.rank = rank; c.world = world;
@@ -1240,6 +1309,7 @@ int smle_dist_create(smle_dist_t *out, smle_csr_t local_a, int rank, int world, 
     for (int q = 0; q <= world; ++q) c.send_off[q] = send_off[q];
     for (int q = 0; q < world; ++q) { c.send_dst[q] = send_dst[q]; c.needs_from[q] = needs_from[q]; }
     c.ticket = d->ticket;
+    c.stop = local_a->ws.ctrl + CTRL_STOP;
     {   // fused push: possible when every send group is one ascending run of consecutive local rows
         static int allow = -1;
         if (allow < 0) { const char *e = getenv("SMLE_DIST_FUSED_PUSH"); allow = e ? atoi(e) : 1; }
@@ -1261,6 +1331,44 @@ int smle_dist_create(smle_dist_t *out, smle_csr_t local_a, int rank, int world, 
     c.peer_p[rank] = dist_p(d);
     d->peer_base[rank] = d->comm;
     d->connected = false;   // smle_dist_connect finishes the setup (also for world == 1)
+    return SMLE_OK;
+}
+
+} // namespace
+
+extern "C" {
+
+int smle_dist_bounds(const int *row_offsets, int m, int world, int *bounds)
+{
+    if (!row_offsets || m < 0 || world < 1 || !bounds) return fail(SMLE_ERR_ARG, "smle_dist_bounds: bad argument");
+    std::vector<int> xy(2 * ((size_t)world + 1));
+    int rc = smle_merge_path_partition(row_offsets + 1, m, row_offsets[m], world, 0, xy.data());
+    if (rc) return rc;
+    for (int g = 0; g <= world; ++g) bounds[g] = xy[2 * (size_t)g];   // a row cut mid-way belongs whole to the later part
+    bounds[0] = 0;
+    bounds[world] = m;
+    return SMLE_OK;
+}
+
+int smle_dist_create_from_plan(smle_dist_t *out, smle_plan_t plan, const double *local_values)
+{
+    if (!out || !plan) return fail(SMLE_ERR_ARG, "smle_dist_create_from_plan: bad argument");
+    const smle_plan_s &p = *plan;
+    if (!p.finished) return fail(SMLE_ERR_ARG, "smle_dist_plan_finish has not been called");
+    if (p.world > kMaxRanks) return fail(SMLE_ERR_ARG, "world %d exceeds the %d ranks of the peer-memory control block", p.world, kMaxRanks);
+    if (p.nnz_local > 0 && !local_values) return fail(SMLE_ERR_ARG, "local_values is NULL");
+    int rc = ensure_init();
+    if (rc) return rc;
+    smle_csr_t a = nullptr;
+    rc = csr_create<double>(&a, p.n_local, p.halo_base + p.n_halo, p.nnz_local, p.lro.data(), p.lci.data(), local_values);
+    if (rc) return rc;
+    smle_dist_t d = nullptr;
+    rc = dist_create(&d, a, p.rank, p.world, p.n_local, p.n_halo, p.halo_base, p.send_off.data(), p.send_idx.data(),
+                     p.send_dst.data(), p.needs_from.data());
+    if (rc) {
+        if (d) smle_dist_destroy(d); else smle_csr_destroy(a);
+        return rc;
+    }
     *out = d;
     return SMLE_OK;
 }
@@ -1277,7 +1385,7 @@ int smle_dist_ipc_handle(smle_dist_t d, unsigned char *out64)
 
 int smle_dist_connect(smle_dist_t d, const unsigned char *all_handles)
 {
-    if (!d || !all_handles) return fail(SMLE_ERR_ARG, "bad argument");
+    if (!d || (!all_handles && d->world > 1)) return fail(SMLE_ERR_ARG, "bad argument");
     for (int q = 0; q < d->world; ++q) {
         if (q == d->rank) continue;
         cudaIpcMemHandle_t h;
@@ -1303,11 +1411,23 @@ void smle_dist_destroy(smle_dist_t d)
     for (int q = 0; q < d->world; ++q)
         if (q != d->rank && d->peer_base[q]) cudaIpcCloseMemHandle(d->peer_base[q]);
     cudaFree(d->comm); cudaFree(d->send_idx); cudaFree(d->ticket); cudaFree(d->ctl_dev);
+    cudaFree(d->b_stage); cudaFree(d->x_stage);
+    if (d->a) smle_csr_destroy(d->a);
     delete d;
 }
 
-// y_local = (A x)_local : pushes/receives the halo of x, then the local merge-path SpMV.
-// Collective: every rank of the partition must call it.
+int smle_dist_dims(smle_dist_t d, int *n_local, int *n_halo, int *rank, int *world)
+{
+    if (!d) return fail(SMLE_ERR_ARG, "null handle");
+    if (n_local) *n_local = d->n_local;
+    if (n_halo) *n_halo = d->n_halo;
+    if (rank) *rank = d->rank;
+    if (world) *world = d->world;
+    return SMLE_OK;
+}
+
+// y_local = (A x)_local : pushes the halo of x, then the local merge-path SpMV whose boundary tiles
+// wait for the neighbours' pushes.  Collective: every rank of the partition must call it.
 int smle_dist_spmv_f64(smle_dist_t d, const double *x_local_dev, double *y_local_dev)
 {
     if (!d || !x_local_dev || !y_local_dev) return fail(SMLE_ERR_ARG, "bad argument");
@@ -1318,34 +1438,49 @@ int smle_dist_spmv_f64(smle_dist_t d, const double *x_local_dev, double *y_local
     int ctrl[CTRL_WORDS] = {0, 0, 0, 1, 0, d->seq_base, 0, 0};
     CU(cudaMemcpyAsync(w.ctrl, ctrl, sizeof(ctrl), cudaMemcpyHostToDevice, g_stream));
     CU(cudaMemcpyAsync(dist_p(d), x_local_dev, sizeof(double) * (size_t)d->n_local, cudaMemcpyDeviceToDevice, g_stream));
-    int total = d->ctl.send_off[d->world];
-    int pgrid = (total + kThreads - 1) / kThreads;
-    if (pgrid < 1) pgrid = 1;
-    if (pgrid > g_sms) pgrid = g_sms;
-    dist_halo_push_kernel<<<pgrid, kThreads, 0, g_stream>>>(d->ctl, dist_p(d), w.ctrl);
+    dist_halo_push_kernel<<<dist_push_grid(d), kThreads, 0, g_stream>>>(d->ctl, dist_p(d), w.ctrl);
     ++g_launches;
     rc = check_launch("dist_halo_push_kernel");
     if (rc) return rc;
     d->seq_base += 2;
-    CgScalars none = {};
-    return launch_merge<double, false>(d->a, dist_p(d), y_local_dev, 1, none);
+    CgScalars cg = make_scalars(w, 1);   // the boundary tiles read the sequence base from ctrl
+    g_spmv_dist = d->ctl_dev;
+    rc = launch_merge<double, false>(d->a, dist_p(d), y_local_dev, 1, cg);
+    g_spmv_dist = nullptr;
+    if (rc) return rc;
+    int err = 0;
+    CU(cudaMemcpyAsync(&err, &d->ctl.self->error, sizeof(int), cudaMemcpyDeviceToHost, g_stream));
+    CU(cudaStreamSynchronize(g_stream));
+    if (err) return fail(SMLE_ERR_COMM, "a peer did not answer (halo wait timed out)");
+    return SMLE_OK;
 }
 
 // Row-partitioned CGSolveSingle (single_strategy.hpp:105-170 semantics on the global system).
-// b_local / x_local: this rank's rows, device pointers.  Collective over the partition.
-int smle_dist_cg_f64(smle_dist_t d, const double *b_local_dev, double *x_local_dev, int max_iters, double tol,
-                     int *iters_out, double *final_rel_res)
+// b_local / x_local: this rank's rows (device pointers, or host pointers with is_device_ptr = 0).
+// Collective over the partition.
+int smle_dist_cg_f64(smle_dist_t d, const double *b_local, double *x_local, int max_iters, double tol,
+                     int is_device_ptr, int *iters_out, double *final_rel_res)
 {
-    if (!d || !b_local_dev || !x_local_dev) return fail(SMLE_ERR_ARG, "bad argument");
+    if (!d || !b_local || !x_local) return fail(SMLE_ERR_ARG, "bad argument");
     if (!d->connected) return fail(SMLE_ERR_COMM, "smle_dist_connect has not been called");
     smle_csr_t a = d->a;
     int rc = ensure_workspace(a, 1, 0);
     if (!rc) rc = ensure_scratch(a, 1);
     if (rc) return rc;
+    const size_t vb = sizeof(double) * (size_t)(d->n_local > 0 ? d->n_local : 1);
+    const double *b_dev = b_local;
+    double *x_dev = x_local;
+    if (!is_device_ptr) {
+        if (!d->b_stage) CU(cudaMalloc(&d->b_stage, vb));
+        if (!d->x_stage) CU(cudaMalloc(&d->x_stage, vb));
+        CU(cudaMemcpyAsync(d->b_stage, b_local, sizeof(double) * (size_t)d->n_local, cudaMemcpyHostToDevice, g_stream));
+        b_dev = d->b_stage;
+        x_dev = d->x_stage;
+    }
     CgWorkspace &w = a->ws;
     CgScalars cg = make_scalars(w, 1);
     CgVecArgs va;
-    va.B = b_local_dev; va.X = w.Xd; va.R = w.R; va.P = dist_p(d); va.AP = w.AP;
+    va.B = b_dev; va.X = w.Xd; va.R = w.R; va.P = dist_p(d); va.AP = w.AP;
     va.n = d->n_local; va.k = 1; va.part = w.part; va.ticket = a->ticket + 1;
 
     // init: x = 0, r = p = b, local b.b -> all-reduce -> rs_old, bnorm; first halo push
@@ -1359,8 +1494,14 @@ int smle_dist_cg_f64(smle_dist_t d, const double *b_local_dev, double *x_local_d
     if (rc) return rc;
 
     const bool use_graph = getenv("SMLE_NO_GRAPH") == nullptr;
+    if (d->graph && d->graph_epoch != a->scratch_epoch) {   // scratch was reallocated since the capture
+        cudaGraphExecDestroy(d->graph);
+        d->graph = nullptr;
+    }
     if (use_graph && !d->graph) {
+        g_spmv_dist = d->ctl_dev;   // the dry run must size the same partition (with halo flags) the solve uses
         rc = launch_merge<double, true>(a, va.P, va.AP, 1, cg, /*dry=*/true);
+        g_spmv_dist = nullptr;
         if (rc) return rc;
         cudaGraph_t graph;
         CU(cudaStreamBeginCapture(g_stream, cudaStreamCaptureModeThreadLocal));
@@ -1372,6 +1513,7 @@ int smle_dist_cg_f64(smle_dist_t d, const double *b_local_dev, double *x_local_d
         e = cudaGraphInstantiate(&d->graph, graph, 0);
         cudaGraphDestroy(graph);
         if (e != cudaSuccess) return fail(SMLE_ERR_CUDA, "graph instantiate failed: %s", cudaGetErrorString(e));
+        d->graph_epoch = a->scratch_epoch;
     }
     const int batch = use_graph ? kGraphIters : 4;
     const long long per_iter = d->ctl.fused ? 3LL : 4LL;
@@ -1388,17 +1530,17 @@ int smle_dist_cg_f64(smle_dist_t d, const double *b_local_dev, double *x_local_d
         return SMLE_OK;
     });
     if (rc) return rc;
-    CU(cudaMemcpyAsync(x_local_dev, w.Xd, sizeof(double) * (size_t)d->n_local, cudaMemcpyDeviceToDevice, g_stream));
+    if (is_device_ptr) CU(cudaMemcpyAsync(x_dev, w.Xd, sizeof(double) * (size_t)d->n_local, cudaMemcpyDeviceToDevice, g_stream));
+    else CU(cudaMemcpyAsync(x_local, w.Xd, sizeof(double) * (size_t)d->n_local, cudaMemcpyDeviceToHost, g_stream));
     CU(cudaMemcpyAsync(w.ctrl_host, w.ctrl, sizeof(int) * CTRL_WORDS, cudaMemcpyDeviceToHost, g_stream));
     CU(cudaMemcpyAsync(w.ctrl_host + CTRL_WORDS, cg.last_rel, sizeof(double), cudaMemcpyDeviceToHost, g_stream));
-    int err = 0;
-    CU(cudaMemcpyAsync(&err, &d->ctl.self->error, sizeof(int), cudaMemcpyDeviceToHost, g_stream));
+    CU(cudaMemcpyAsync(w.ctrl_host + CTRL_WORDS + 2, &d->ctl.self->error, sizeof(int), cudaMemcpyDeviceToHost, g_stream));
     CU(cudaStreamSynchronize(g_stream));
     const int iters = w.ctrl_host[CTRL_ITER];
     d->seq_base += iters + 2;
     if (iters_out) *iters_out = iters;
     if (final_rel_res) memcpy(final_rel_res, w.ctrl_host + CTRL_WORDS, sizeof(double));
-    if (err) return fail(SMLE_ERR_COMM, "a peer did not answer (spin-wait timeout)");
+    if (w.ctrl_host[CTRL_WORDS + 2]) return fail(SMLE_ERR_COMM, "a peer did not answer (wait timed out)");
     return SMLE_OK;
 }
 

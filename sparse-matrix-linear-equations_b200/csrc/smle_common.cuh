@@ -230,4 +230,95 @@ __device__ __forceinline__ void cta_reduce_columns(const V *src1, const V *src2,
     __syncthreads();
 }
 
+// ---------------------------------------------------------------------------------------
+// Carry slots: a bit pattern no arithmetic result can have marks an empty slot.
+// ---------------------------------------------------------------------------------------
+template <typename V> struct CarrySentinel;
+template <> struct CarrySentinel<double> { static constexpr unsigned long long bits = 0xFFF75EA1C0DED00Dull; };
+template <> struct CarrySentinel<float> { static constexpr unsigned int bits = 0xFFA5C0DEu; };
+
+template <typename V>
+__device__ __forceinline__ bool is_sentinel(V v)
+{
+    if constexpr (sizeof(V) == 8) return (unsigned long long)__double_as_longlong(v) == CarrySentinel<double>::bits;
+    else return __float_as_uint(v) == CarrySentinel<float>::bits;
+}
+
+template <typename V>
+__device__ __forceinline__ V sentinel_value()
+{
+    if constexpr (sizeof(V) == 8) return __longlong_as_double((long long)CarrySentinel<double>::bits);
+    else return __uint_as_float(CarrySentinel<float>::bits);
+}
+
+template <typename V>
+__global__ void fill_sentinel_kernel(V *p, size_t count)
+{
+    const V s = sentinel_value<V>();
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (size_t)gridDim.x * blockDim.x)
+        p[i] = s;
+}
+
+// ---- wait-free carry exchange ------------------------------------------------------------------
+// Slot t holds the sentinel until one of the two parties of the row cut by the boundary between
+// tiles t and t+1 arrives: the tile that has the row's leading part (publisher) or the tile the
+// row continues in (owner).  Each swaps its value in; whoever finds the other's value there
+// finishes the row (owner part + carry, the reference's order) and re-arms the slot.  Nobody
+// ever waits, so the schedule of tiles over CTAs is free.
+template <typename V>
+__device__ __forceinline__ V slot_exchange(V *slot, V mine)
+{
+    if constexpr (sizeof(V) == 8) {
+        const unsigned long long o = atomicExch(reinterpret_cast<unsigned long long *>(slot),
+                                                (unsigned long long)__double_as_longlong(mine));
+        return __longlong_as_double((long long)o);
+    } else {
+        const unsigned int o = atomicExch(reinterpret_cast<unsigned int *>(slot), __float_as_uint(mine));
+        return __uint_as_float(o);
+    }
+}
+
+template <typename V>
+__device__ __forceinline__ void slot_reset(V *slot)
+{
+    *reinterpret_cast<volatile V *>(slot) = sentinel_value<V>();
+}
+
+// ---------------------------------------------------------------------------------------
+// Single-column variant of the reduction above (k = 1 kernels): a fixed shuffle tree instead of a
+// serial pass of one thread over blockDim.x shared-memory values (~2 us on the critical path of
+// every CG kernel's last CTA).  Order fixed by (blockDim.x, entries): deterministic.  All threads
+// of the CTA must call it; every thread returns the total.  red: >= 33 values of shared scratch.
+// ---------------------------------------------------------------------------------------
+template <typename V>
+__device__ __forceinline__ V cta_reduce_one(const V *src1, const V *src2, int entries, V *red)
+{
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = (blockDim.x + 31) >> 5;
+    V s = 0;
+    for (int e = tid; e < entries; e += blockDim.x) {
+        s += __ldcg(src1 + e);
+        if (src2) s += __ldcg(src2 + e);
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
+    __syncthreads();
+    if (lane == 0) red[warp] = s;
+    __syncthreads();
+    if (warp == 0) {
+        V t = lane < nw ? red[lane] : V(0);
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) t += __shfl_xor_sync(0xffffffffu, t, d);
+        if (lane == 0) red[32] = t;
+    }
+    __syncthreads();
+    return red[32];
+}
+
+__device__ __forceinline__ unsigned long long global_timer_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+
 } // namespace smle

@@ -6,15 +6,16 @@
 //
 //   * halo exchange: after p is updated, every rank PUSHES the entries its neighbours need
 //     straight into the halo tail of their p vector (peer pointers from CUDA IPC, stores over
-//     NVLink), fences, publishes a sequence number in the neighbour's memory, and waits for
-//     its own incoming sequence numbers;
+//     NVLink), fences and publishes a sequence number in the neighbour's memory; only the BOUNDARY
+//     TILES of the next SpMV wait for the incoming numbers, its interior tiles start at once;
 //   * dot products: every rank posts its partial sum into a mailbox slot in EVERY peer's memory;
-//     the consuming kernel spins on its local mailbox and adds the G values in rank order, so
-//     all ranks obtain bit-identical alpha / beta / convergence decisions with one NVLink
-//     write latency instead of a collective call.
+//     one warp of every CTA of the consuming kernel polls its local mailbox (lane q <- rank q) and
+//     adds the G values in rank order, so all ranks obtain bit-identical alpha / beta /
+//     convergence decisions with one NVLink write latency instead of a collective call
+//     (flag-in-data slots: smle_distctl.cuh).
 //
 // Sequence numbers are derived from the device-resident iteration counter, so the whole
-// iteration (6 launches) replays from one CUDA graph.  Mailbox slots are double-buffered by
+// iteration (3 or 4 launches) replays from one CUDA graph.  Mailbox slots are double-buffered by
 // iteration parity; the reduction dependency chain keeps ranks within one step of each other,
 // which makes the reuse safe.
 #pragma once
@@ -31,7 +32,9 @@ __global__ void dist_post_kernel(DistCtl d, int kind, const double *value, const
     dist_post(d, kind, *value, ctrl);
 }
 
-// K2 (distributed): alpha from the all-reduced p.Ap, r -= alpha*Ap, local r.r -> cg.rs_new[0]
+// K2 (distributed): alpha from the all-reduced p.Ap, r -= alpha*Ap, local r.r posted to every rank.
+// The first batch of r / Ap is requested BEFORE the mailbox wait, so the NVLink latency of the
+// reduction overlaps the DRAM latency of the sweep's first loads.
 __global__ void __launch_bounds__(kThreads)
 cg1d_update_r_kernel(CgVecArgs a, CgScalars cg, DistCtl d)
 {
@@ -39,28 +42,34 @@ cg1d_update_r_kernel(CgVecArgs a, CgScalars cg, DistCtl d)
     __shared__ double s_alpha;
     if (cg.ctrl[CTRL_STOP]) return;
     const int tid = threadIdx.x;
-    if (tid == 0) {
-        const int it = cg.ctrl[CTRL_ITER];
-        const double pAp = dist_wait_sum(d, 0, it & 1, (unsigned long long)cg.ctrl[CTRL_SEQ_BASE] + (unsigned long long)it + 1ull);
-        s_alpha = cg.rs_old[0] / pAp;
-        if (blockIdx.x == 0) cg.alpha[0] = s_alpha;
-    }
-    __syncthreads();
     const uint64_t pol_first = make_policy_evict_first(), pol_last = make_policy_evict_last();
-    const double na = -s_alpha;
     const long long n2 = a.n >> 1;
     const long long stride = (long long)gridDim.x * kThreads;
-    double s = 0.0;
-    for (long long i = (long long)blockIdx.x * kThreads + tid; i < n2; i += stride * kVecUnroll) {
-        double2 r[kVecUnroll], ap[kVecUnroll];
+    long long i = (long long)blockIdx.x * kThreads + tid;
+    double2 r[kVecUnroll], ap[kVecUnroll];
+    auto load = [&](long long base) {
 #pragma unroll
         for (int u = 0; u < kVecUnroll; ++u) {
-            const long long j = i + u * stride;
+            const long long j = base + u * stride;
             if (j < n2) {
                 r[u] = ld_f64x2_hint(a.R + 2 * j, pol_last);
                 ap[u] = ld_f64x2_hint(a.AP + 2 * j, pol_first);
             }
         }
+    };
+    if (i < n2) load(i);
+    if (tid < 32) {
+        const int it = cg.ctrl[CTRL_ITER];
+        const double pAp = dist_wait_sum(d, 0, it & 1, dist_mail_seq(cg.ctrl, 0, it));
+        if (tid == 0) {
+            s_alpha = cg.rs_old[0] / pAp;
+            if (blockIdx.x == 0) cg.alpha[0] = s_alpha;
+        }
+    }
+    __syncthreads();
+    const double na = -s_alpha;
+    double s = 0.0;
+    while (i < n2) {
 #pragma unroll
         for (int u = 0; u < kVecUnroll; ++u) {
             const long long j = i + u * stride;
@@ -72,12 +81,14 @@ cg1d_update_r_kernel(CgVecArgs a, CgScalars cg, DistCtl d)
                 st_f64x2_hint(a.R + 2 * j, r[u], pol_last);
             }
         }
+        i += stride * kVecUnroll;
+        if (i < n2) load(i);
     }
     if ((a.n & 1) && blockIdx.x == 0 && tid == 0) {
         const int j = a.n - 1;
-        double r = a.R[j] + na * a.AP[j];
-        a.R[j] = r;
-        s += r * r;
+        double rj = a.R[j] + na * a.AP[j];
+        a.R[j] = rj;
+        s += rj * rj;
     }
 #pragma unroll
     for (int dd = 16; dd > 0; dd >>= 1) s += __shfl_xor_sync(0xffffffffu, s, dd);
@@ -85,18 +96,22 @@ cg1d_update_r_kernel(CgVecArgs a, CgScalars cg, DistCtl d)
     __syncthreads();
     if (tid == 0) {
         double t = 0;
-        for (int i = 0; i < kWarps; ++i) t += s_red[i];
+        for (int w = 0; w < kWarps; ++w) t += s_red[w];
         a.part[blockIdx.x] = t;
     }
     if (!last_cta_election(a.ticket, gridDim.x)) return;
-    cta_reduce_columns<double>(a.part, nullptr, gridDim.x, 1, cg.rs_new, s_red);   // local r.r
-    dist_post(d, 1, cg.rs_new[0], cg.ctrl);                                        // -> every peer's mailbox
+    const double rr = cta_reduce_one<double>(a.part, nullptr, gridDim.x, s_red);   // local r.r
+    if (tid == 0) cg.rs_new[0] = rr;
+    dist_post(d, 1, rr, cg.ctrl);                                                   // -> every rank's mailbox
 }
 
 // K3 (distributed).  mode 0: beta / convergence from the all-reduced r.r, x += alpha p,
 // p = r + beta p (grid-stride: all CTAs sweep one moving window, which keeps the five HBM streams
-// page-friendly -- a per-CTA chunked sweep measured 20 % slower); the last CTA advances the
-// iteration state.  mode 1 (after cg_init_kernel): b.b all-reduce -> rs_old / bnorm.
+// page-friendly -- a per-CTA chunked sweep measured 20 % slower); rows on the slab boundary also go
+// straight into the neighbours' halo tails (fused push).  The last CTA publishes the halo sequence
+// numbers and advances the iteration state; it does NOT wait for the neighbours -- the next SpMV's
+// boundary tiles do (dist_wait_halo), its interior tiles start at once.
+// mode 1 (after cg_init_kernel): b.b all-reduce -> rs_old / bnorm.
 __global__ void __launch_bounds__(kThreads)
 cg1d_update_xp_kernel(CgVecArgs a, CgScalars cg, DistCtl d, int mode)
 {
@@ -104,39 +119,44 @@ cg1d_update_xp_kernel(CgVecArgs a, CgScalars cg, DistCtl d, int mode)
     __shared__ int s_final, s_it;
     if (cg.ctrl[CTRL_STOP]) return;
     const int tid = threadIdx.x;
-    if (tid == 0) {
+    const uint64_t pol_first = make_policy_evict_first(), pol_last = make_policy_evict_last();
+    const long long n2 = a.n >> 1;
+    const long long stride = (long long)gridDim.x * kThreads;
+    long long i = (long long)blockIdx.x * kThreads + tid;
+    double2 x[kVecUnroll], p[kVecUnroll], r[kVecUnroll];
+    auto load = [&](long long base) {
+#pragma unroll
+        for (int u = 0; u < kVecUnroll; ++u) {
+            const long long j = base + u * stride;
+            if (j < n2) {
+                x[u] = ld_f64x2_hint(a.X + 2 * j, pol_first);
+                p[u] = ld_f64x2_hint(a.P + 2 * j, pol_last);
+                r[u] = ld_f64x2_hint(a.R + 2 * j, pol_last);
+            }
+        }
+    };
+    if (mode == 0 && i < n2) load(i);   // in flight while the reduction arrives
+    if (tid < 32) {
         const int it = cg.ctrl[CTRL_ITER];
-        s_it = it;
         if (mode == 1) {
-            s_rr = dist_wait_sum(d, 2, 0, (unsigned long long)cg.ctrl[CTRL_SEQ_BASE] + 1ull);
-            s_beta = 0.0;
-            s_final = 0;
+            const double bb = dist_wait_sum(d, 2, 0, dist_mail_seq(cg.ctrl, 2, 0));
+            if (tid == 0) { s_it = it; s_rr = bb; s_beta = 0.0; s_final = 0; }
         } else {
-            const double rr = dist_wait_sum(d, 1, it & 1, (unsigned long long)cg.ctrl[CTRL_SEQ_BASE] + (unsigned long long)it + 1ull);
-            const double rel = sqrt(rr) / cg.bnorm[0];
-            s_rr = rr;
-            s_beta = rr / cg.rs_old[0];
-            s_final = (rel < *cg.tol) || (it + 1 >= cg.ctrl[CTRL_MAX_ITERS]);
+            const double rr = dist_wait_sum(d, 1, it & 1, dist_mail_seq(cg.ctrl, 1, it));
+            if (tid == 0) {
+                const double rel = sqrt(rr) / cg.bnorm[0];
+                s_it = it;
+                s_rr = rr;
+                s_beta = rr / cg.rs_old[0];
+                s_final = (rel < *cg.tol) || (it + 1 >= cg.ctrl[CTRL_MAX_ITERS]);
+            }
         }
     }
     __syncthreads();
     if (mode == 0) {
         const bool final_iter = s_final != 0;
-        const uint64_t pol_first = make_policy_evict_first(), pol_last = make_policy_evict_last();
         const double al = cg.alpha[0], be = s_beta;
-        const long long n2 = a.n >> 1;
-        const long long stride = (long long)gridDim.x * kThreads;
-        for (long long i = (long long)blockIdx.x * kThreads + tid; i < n2; i += stride * kVecUnroll) {
-            double2 x[kVecUnroll], p[kVecUnroll], r[kVecUnroll];
-#pragma unroll
-            for (int u = 0; u < kVecUnroll; ++u) {
-                const long long j = i + u * stride;
-                if (j < n2) {
-                    x[u] = ld_f64x2_hint(a.X + 2 * j, pol_first);
-                    p[u] = ld_f64x2_hint(a.P + 2 * j, pol_last);
-                    if (!final_iter) r[u] = ld_f64x2_hint(a.R + 2 * j, pol_last);
-                }
-            }
+        while (i < n2) {
 #pragma unroll
             for (int u = 0; u < kVecUnroll; ++u) {
                 const long long j = i + u * stride;
@@ -160,6 +180,8 @@ cg1d_update_xp_kernel(CgVecArgs a, CgScalars cg, DistCtl d, int mode)
                     }
                 }
             }
+            i += stride * kVecUnroll;
+            if (i < n2) load(i);
         }
         if ((a.n & 1) && blockIdx.x == 0 && tid == 0) {
             const int j = a.n - 1;
@@ -179,15 +201,10 @@ cg1d_update_xp_kernel(CgVecArgs a, CgScalars cg, DistCtl d, int mode)
     }
     if (!last_cta_election(a.ticket, gridDim.x)) return;
     if (mode == 0 && d.fused && !s_final) {
-        // halo of the p for iteration it+1: tell the neighbours, then wait for theirs, so that the next
-        // SpMV starts (kernel boundary) with a complete halo
+        // the halo of the p for iteration it+1 has left: tell the neighbours
         const unsigned long long seq = (unsigned long long)cg.ctrl[CTRL_SEQ_BASE] + (unsigned long long)s_it + 2ull;
         const int q = tid;
-        if (q < d.world && q != d.rank) {
-            if (d.send_off[q + 1] > d.send_off[q]) st_release_sys(&d.peer[q]->halo_seq[d.rank], seq);
-            if (d.needs_from[q]) dist_spin(&d.self->halo_seq[q], seq, &d.self->error);
-        }
-        __syncthreads();
+        if (q < d.world && q != d.rank && d.send_off[q + 1] > d.send_off[q]) st_release_sys(&d.peer[q]->halo_seq[d.rank], seq);
     }
     if (tid == 0) {
         if (mode == 1) {
@@ -195,7 +212,7 @@ cg1d_update_xp_kernel(CgVecArgs a, CgScalars cg, DistCtl d, int mode)
             cg.rs_old[0] = s_rr;
             cg.bnorm[0] = nb == 0.0 ? 1.0 : nb;
         } else {
-            const int it = cg.ctrl[CTRL_ITER];
+            const int it = s_it;
             const double rel = sqrt(s_rr) / cg.bnorm[0];
             if (cg.hist && it < cg.hist_cap) cg.hist[it] = rel;
             *cg.last_rel = rel;
@@ -207,8 +224,8 @@ cg1d_update_xp_kernel(CgVecArgs a, CgScalars cg, DistCtl d, int mode)
     }
 }
 
-// Halo push: P[send_idx] -> the halo tail of each neighbour's p vector (NVLink peer stores), then
-// sequence numbers, then wait for the neighbours' pushes.  When it retires, the next SpMV can start.
+// Halo push: P[send_idx] -> the halo tail of each neighbour's p vector (NVLink peer stores), then the
+// sequence numbers.  The consumers of the halo (boundary tiles of the next SpMV) wait for them.
 __global__ void __launch_bounds__(kThreads)
 dist_halo_push_kernel(DistCtl d, const double *__restrict__ P, const int *ctrl)
 {
@@ -223,10 +240,7 @@ dist_halo_push_kernel(DistCtl d, const double *__restrict__ P, const int *ctrl)
     __threadfence_system();
     if (!last_cta_election(d.ticket, gridDim.x)) return;
     const int q = threadIdx.x;
-    if (q < d.world && q != d.rank) {
-        if (d.send_off[q + 1] > d.send_off[q]) st_release_sys(&d.peer[q]->halo_seq[d.rank], seq);
-        if (d.needs_from[q]) dist_spin(&d.self->halo_seq[q], seq, &d.self->error);
-    }
+    if (q < d.world && q != d.rank && d.send_off[q + 1] > d.send_off[q]) st_release_sys(&d.peer[q]->halo_seq[d.rank], seq);
 }
 
 } // namespace smle

@@ -68,21 +68,40 @@ int gen_grid2d(int w, int self_loop, V diag, V offd, int *ro, int *ci, V *va)
 
 // 3-D grid: me=(i,j,k); sorted neighbours me-w^2, me-w, me-1, [me], me+1, me+w, me+w^2
 // (sparse_matrix.h:533-623 emits -k,+k,-j,+j,-i,+i,self)
-template <typename V>
-int gen_grid3d(int w, int self_loop, V diag, V offd, int *ro, int *ci, V *va)
+inline int grid3d_degree(int w, int ww, int me, int self_loop)
 {
-    if (w < 1 || !ro || !ci || !va) return SMLE_ERR_ARG;
+    const int i = me / ww, j = (me / w) % w, k = me % w;
+    return (i > 0) + (j > 0) + (k > 0) + (k + 1 < w) + (j + 1 < w) + (i + 1 < w) + (self_loop ? 1 : 0);
+}
+
+int gen_grid3d_row_offsets(int w, int self_loop, int *ro)
+{
+    if (w < 1 || !ro) return SMLE_ERR_ARG;
     const int ww = w * w, m = ww * w;
 #pragma omp parallel for schedule(static)
-    for (int me = 0; me < m; ++me) {
-        int i = me / ww, j = (me / w) % w, k = me % w;
-        ro[me + 1] = (i > 0) + (j > 0) + (k > 0) + (k + 1 < w) + (j + 1 < w) + (i + 1 < w) + (self_loop ? 1 : 0);
-    }
+    for (int me = 0; me < m; ++me) ro[me + 1] = grid3d_degree(w, ww, me, self_loop);
     ro[0] = 0;
     for (int r = 0; r < m; ++r) ro[r + 1] += ro[r];
+    return SMLE_OK;
+}
+
+// rows [r0, r1): local offsets from 0, global column indices
+template <typename V>
+int gen_grid3d_rows(int w, int self_loop, V diag, V offd, int r0, int r1, int *lro, int *ci, V *va)
+{
+    if (w < 1 || !lro) return SMLE_ERR_ARG;
+    const int ww = w * w, m = ww * w;
+    if (r0 < 0 || r1 < r0 || r1 > m) return SMLE_ERR_ARG;
+    const int n = r1 - r0;
 #pragma omp parallel for schedule(static)
-    for (int me = 0; me < m; ++me) {
-        int i = me / ww, j = (me / w) % w, k = me % w, z = ro[me];
+    for (int l = 0; l < n; ++l) lro[l + 1] = grid3d_degree(w, ww, r0 + l, self_loop);
+    lro[0] = 0;
+    for (int l = 0; l < n; ++l) lro[l + 1] += lro[l];
+    if (lro[n] > 0 && (!ci || !va)) return SMLE_ERR_ARG;
+#pragma omp parallel for schedule(static)
+    for (int l = 0; l < n; ++l) {
+        const int me = r0 + l;
+        int i = me / ww, j = (me / w) % w, k = me % w, z = lro[l];
         if (i > 0)      { ci[z] = me - ww; va[z++] = offd; }
         if (j > 0)      { ci[z] = me - w;  va[z++] = offd; }
         if (k > 0)      { ci[z] = me - 1;  va[z++] = offd; }
@@ -92,6 +111,13 @@ int gen_grid3d(int w, int self_loop, V diag, V offd, int *ro, int *ci, V *va)
         if (i + 1 < w)  { ci[z] = me + ww; va[z++] = offd; }
     }
     return SMLE_OK;
+}
+
+template <typename V>
+int gen_grid3d(int w, int self_loop, V diag, V offd, int *ro, int *ci, V *va)
+{
+    if (w < 1 || !ro || !ci || !va) return SMLE_ERR_ARG;
+    return gen_grid3d_rows<V>(w, self_loop, diag, offd, 0, w * w * w, ro, ci, va);
 }
 
 // wheel (sparse_matrix.h:417-450): hub row 0 -> 1..s; rim row i+1 -> ((i+1) % s) + 1
@@ -221,6 +247,16 @@ int smle_gen_grid2d_f64(int w, int sl, double d, double o, int *ro, int *ci, dou
 int smle_gen_grid2d_f32(int w, int sl, float d, float o, int *ro, int *ci, float *va) { return gen_grid2d<float>(w, sl, d, o, ro, ci, va); }
 int smle_gen_grid3d_f64(int w, int sl, double d, double o, int *ro, int *ci, double *va) { return gen_grid3d<double>(w, sl, d, o, ro, ci, va); }
 int smle_gen_grid3d_f32(int w, int sl, float d, float o, int *ro, int *ci, float *va) { return gen_grid3d<float>(w, sl, d, o, ro, ci, va); }
+int smle_gen_grid3d_row_offsets(int w, int sl, int *ro)
+{
+    if (w < 1 || (long long)w * w * w * 7 > INT32_MAX) return SMLE_ERR_ARG;
+    return gen_grid3d_row_offsets(w, sl, ro);
+}
+int smle_gen_grid3d_rows_f64(int w, int sl, double d, double o, int r0, int r1, int *lro, int *ci, double *va)
+{
+    if (w < 1 || (long long)w * w * w * 7 > INT32_MAX) return SMLE_ERR_ARG;
+    return gen_grid3d_rows<double>(w, sl, d, o, r0, r1, lro, ci, va);
+}
 int smle_gen_wheel_f64(int s, double v, int *ro, int *ci, double *va) { return gen_wheel<double>(s, v, ro, ci, va); }
 int smle_gen_wheel_f32(int s, float v, int *ro, int *ci, float *va) { return gen_wheel<float>(s, v, ro, ci, va); }
 int smle_gen_dense_f64(int r, int c, double v, int *ro, int *ci, double *va) { return gen_dense<double>(r, c, v, ro, ci, va); }
@@ -238,6 +274,15 @@ int smle_gen_rhs_rand_f64(unsigned seed, long long count, double *out)
 {
     if (count < 0 || (count > 0 && !out)) return SMLE_ERR_ARG;
     srand(seed);
+    for (long long i = 0; i < count; ++i) out[i] = (double)rand() / (double)RAND_MAX;
+    return SMLE_OK;
+}
+
+int smle_gen_rhs_rand_range_f64(unsigned seed, long long first, long long count, double *out)
+{
+    if (first < 0 || count < 0 || (count > 0 && !out)) return SMLE_ERR_ARG;
+    srand(seed);
+    for (long long i = 0; i < first; ++i) (void)rand();
     for (long long i = 0; i < count; ++i) out[i] = (double)rand() / (double)RAND_MAX;
     return SMLE_OK;
 }

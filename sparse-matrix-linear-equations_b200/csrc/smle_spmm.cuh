@@ -34,32 +34,6 @@
 
 namespace smle {
 
-template <typename V> struct CarrySentinel;
-template <> struct CarrySentinel<double> { static constexpr unsigned long long bits = 0xFFF75EA1C0DED00Dull; };
-template <> struct CarrySentinel<float> { static constexpr unsigned int bits = 0xFFA5C0DEu; };
-
-template <typename V>
-__device__ __forceinline__ bool is_sentinel(V v)
-{
-    if constexpr (sizeof(V) == 8) return (unsigned long long)__double_as_longlong(v) == CarrySentinel<double>::bits;
-    else return __float_as_uint(v) == CarrySentinel<float>::bits;
-}
-
-template <typename V>
-__device__ __forceinline__ V sentinel_value()
-{
-    if constexpr (sizeof(V) == 8) return __longlong_as_double((long long)CarrySentinel<double>::bits);
-    else return __uint_as_float(CarrySentinel<float>::bits);
-}
-
-template <typename V>
-__global__ void fill_sentinel_kernel(V *p, size_t count)
-{
-    const V s = sentinel_value<V>();
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (size_t)gridDim.x * blockDim.x)
-        p[i] = s;
-}
-
 // L2-coherent (volatile) vector access to a carry slot: VEC*sizeof(V) in {4, 8, 16} bytes
 template <typename V, int VEC>
 __device__ __forceinline__ void ld_volatile_vec(V (&out)[VEC], const V *p)
@@ -153,31 +127,6 @@ struct SpmmArgs {
                                        // gathers in flight instead of 4 (1.61 ms vs 1.42 ms; tests/test_sass_shape.py)
 };
 
-
-// ---- wait-free carry exchange ------------------------------------------------------------------
-// Slot t holds the sentinel until one of the two parties of the row cut by the boundary between
-// tiles t and t+1 arrives: the tile that has the row's leading part (publisher) or the tile the
-// row continues in (owner).  Each swaps its value in; whoever finds the other's value there
-// finishes the row (owner part + carry, the reference's order) and re-arms the slot.  Nobody
-// ever waits, so the schedule of tiles over CTAs is free.
-template <typename V>
-__device__ __forceinline__ V slot_exchange(V *slot, V mine)
-{
-    if constexpr (sizeof(V) == 8) {
-        const unsigned long long o = atomicExch(reinterpret_cast<unsigned long long *>(slot),
-                                                (unsigned long long)__double_as_longlong(mine));
-        return __longlong_as_double((long long)o);
-    } else {
-        const unsigned int o = atomicExch(reinterpret_cast<unsigned int *>(slot), __float_as_uint(mine));
-        return __uint_as_float(o);
-    }
-}
-
-template <typename V>
-__device__ __forceinline__ void slot_reset(V *slot)
-{
-    *reinterpret_cast<volatile V *>(slot) = sentinel_value<V>();
-}
 
 // val = sum of the parts of row tile_xy[tt+1].x that lie in tiles <= tt, column c.
 // Returns the row element's share of the dot product X[row,c]*Y[row,c] when it finished the row.

@@ -15,11 +15,15 @@
 //   * phase B: each thread finds its diagonal with the reference's binary search (in shared
 //     memory) and reduces exactly IPT merge items; completed rows go to a shared row buffer,
 //     the first row of every thread waits for its carry-in;
-//   * carries: warp-shuffle segmented scan keyed by row -> per-tile -> per-CTA -> the last CTA
-//     to finish applies the per-CTA carries in CTA order (merge_based.hpp:137-149 semantics);
+//   * carries: warp-shuffle segmented scan keyed by row -> per-tile -> per-CTA; the row cut by a
+//     CTA boundary is finished wait-free through one global slot per boundary (the party that
+//     arrives second adds owner part + carry, merge_based.hpp:137-149 semantics), so a plain SpMV
+//     has no last-CTA epilogue at all;
 //   * phase C: the tile's rows are written to y with coalesced stores; with DOT the products
 //     y[r]*x[r] (the p.Ap of CG) are accumulated from the same registers.
 #pragma once
+#include <type_traits>
+
 #include "smle_common.cuh"
 #include "smle_distctl.cuh"
 #include "smle_merge.cuh"
@@ -100,13 +104,12 @@ struct SpmvArgs {
     const int *__restrict__ tile_maxlen;  // longest in-tile row segment per tile (matrix property)
     int m, nnz;
     int num_tiles, tiles_per_cta;
-    int *carry_row;                    // [gridDim.x]
-    V *carry_val;                      // [gridDim.x]
+    V *cta_slot;                       // [gridDim.x] carry slots of the CTA boundaries (sentinel when empty)
     V *dot_part;                       // [gridDim.x]  (DOT)
-    V *fix_part;                       // [gridDim.x]  (DOT)
     unsigned int *ticket;
     int debug_flags;                   // 1: skip compute (stream-only ceiling of the TMA pipeline)
-    const DistCtl *dist;               // row-partitioned CG: post the local p.Ap to every peer (else NULL)
+    const DistCtl *dist;               // row-partitioned solve: halo waits, p.Ap posted to every peer (else NULL)
+    const unsigned char *tile_halo;    // row-partitioned solve: 1 for tiles that gather halo columns (else NULL)
 };
 
 template <typename V, int THREADS, int IPT>
@@ -143,6 +146,20 @@ __global__ void tile_maxlen_kernel(const int *__restrict__ ro, const int2 *__res
     }
     mx = __reduce_max_sync(0xffffffffu, mx);
     if (lane == 0) out[t] = mx;
+}
+
+// One warp per tile: does the tile gather a halo column (index >= halo_base)?  Row-partitioned
+// handles only; the flagged tiles wait for the neighbours' halo push before they gather.
+__global__ void tile_halo_kernel(const int *__restrict__ ci, const int2 *__restrict__ tile_xy, int num_tiles,
+                                 int halo_base, unsigned char *__restrict__ out)
+{
+    const int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (t >= num_tiles) return;
+    const int lo = tile_xy[t].y, hi = tile_xy[t + 1].y;
+    int any = 0;
+    for (int z = lo + lane; z < hi; z += 32) any |= __ldg(ci + z) >= halo_base;
+    any = __any_sync(0xffffffffu, any);
+    if (lane == 0) out[t] = any ? 1 : 0;
 }
 
 __global__ void int_max_kernel(const int *__restrict__ v, int n, int *out)
@@ -183,7 +200,14 @@ constexpr int spmv_ctas_per_sm()
 // thread are issued before the first FMA; the value is read from shared memory only when the
 // FMA needs it, which keeps the live registers at 2 per gather.
 // ---------------------------------------------------------------------------------------
-template <typename V>
+template <typename V, bool COH>
+__device__ __forceinline__ V gather(const V *x)
+{
+    // COH: the halo tail of x is written by the peers while this kernel runs -> L2-coherent load
+    if constexpr (COH) return __ldcg(x); else return __ldg(x);
+}
+
+template <typename V, bool COH>
 __device__ __forceinline__ V row_sum(const V *__restrict__ x, const int *pc, const V *pv, int beg, int end)
 {
     constexpr int UB = 8;
@@ -193,13 +217,37 @@ __device__ __forceinline__ V row_sum(const V *__restrict__ x, const int *pc, con
         // hit): no predicate keeps ptxas from issuing all UB requests before the first FMA
         V xa[UB];
 #pragma unroll
-        for (int j = 0; j < UB; ++j) xa[j] = __ldg(x + pc[min(beg + j, end - 1)]);
+        for (int j = 0; j < UB; ++j) xa[j] = gather<V, COH>(x + pc[min(beg + j, end - 1)]);
 #pragma unroll
         for (int j = 0; j < UB; ++j)
             if (beg + j < end) sum += pv[beg + j] * xa[j];
         beg += UB;
     }
     return sum;
+}
+
+// Publisher side of the CTA-boundary exchange.  val = sum of the parts of row R = (row in progress
+// at the end of CTA c) that lie in CTAs <= c.  If the owner's part is already in slot c, finish the
+// row (owner part + carry); if CTA c+1 lies entirely inside the row, add its part and move on.
+template <typename V>
+__device__ __noinline__ void cta_carry_publish(const int2 *__restrict__ tile_xy, int tiles_per_cta, int num_tiles, int m,
+                                               V *cta_slot, V *y, int c, V val)
+{
+    for (;;) {
+        const int row = tile_xy[min((c + 1) * tiles_per_cta, num_tiles)].x;
+        if (row >= m) return;
+        V *slot = cta_slot + c;
+        const V owner = slot_exchange<V>(slot, val);
+        if (is_sentinel<V>(owner)) return;                 // the other party comes later and finishes
+        slot_reset<V>(slot);
+        __threadfence();                                   // its earlier stores to y[row] come before ours
+        if (tile_xy[min((c + 2) * tiles_per_cta, num_tiles)].x > row) {   // the row ends in CTA c+1
+            y[row] = owner + val;
+            return;
+        }
+        val = val + owner;                                 // CTA c+1 lies inside the row: pass on
+        ++c;
+    }
 }
 
 // ---------------------------------------------------------------------------------------
@@ -305,14 +353,22 @@ spmv_kernel(SpmvArgs<V> a, CgScalars cg)
         // tile metadata is fetched one tile ahead so its latency hides behind the previous tile
         int2 nxt_lo = make_int2(0, 0), nxt_hi = make_int2(0, 0);
         int nxt_ml = 0;
-        if (t0 < t1) { nxt_lo = a.tile_xy[t0]; nxt_hi = a.tile_xy[t0 + 1]; nxt_ml = a.tile_maxlen[t0]; }
+        bool nxt_halo = false;
+        if (t0 < t1) {
+            nxt_lo = a.tile_xy[t0]; nxt_hi = a.tile_xy[t0 + 1]; nxt_ml = a.tile_maxlen[t0];
+            if (a.tile_halo) nxt_halo = a.tile_halo[t0] != 0;
+        }
 
         for (int t = t0; t < t1; ++t) {
             const int it = t - t0, s = it % STAGES, slot = it % kChainTiles;
             const uint32_t parity = (uint32_t)(it / STAGES) & 1u;
             const int2 lo = nxt_lo, hi = nxt_hi;
             const int tile_ml = nxt_ml;
-            if (t + 1 < t1) { nxt_lo = hi; nxt_hi = a.tile_xy[t + 2]; nxt_ml = a.tile_maxlen[t + 1]; }
+            const bool tile_halo = nxt_halo;
+            if (t + 1 < t1) {
+                nxt_lo = hi; nxt_hi = a.tile_xy[t + 2]; nxt_ml = a.tile_maxlen[t + 1];
+                if (a.tile_halo) nxt_halo = a.tile_halo[t + 1] != 0;
+            }
             const int x0 = lo.x, y0 = lo.y;
             const int rows = hi.x - x0, nz = hi.y - y0, items = rows + nz;
             const int yc = y0 & ~3, yv = y0 & ~(EPV - 1), rb = (x0 + 1) & ~3;
@@ -325,6 +381,9 @@ spmv_kernel(SpmvArgs<V> a, CgScalars cg)
             if (tid == 0) s_trow[slot] = rows > 0 ? x0 : -1;
 
             mbar_wait(&s_full[s], parity);
+            // row-partitioned solve: only the tiles that gather halo columns wait for the neighbours'
+            // push of this iteration's p; interior tiles never look at the flags
+            if (tile_halo) dist_wait_halo(*a.dist, cg.ctrl);
 
             if (a.debug_flags & 1) {
                 // measurement aid: stream the tile through shared memory and do nothing with it
@@ -332,10 +391,11 @@ spmv_kernel(SpmvArgs<V> a, CgScalars cg)
             } else if (tile_ml <= kRowPathMaxLen) {
                 // ---- regular tile: fused thread-per-row path, no barrier --------------------------------
                 // Pseudo-row `rows` is the trailing part of row hi.x: its sum is the tile carry-out.
+                auto row_path = [&](auto coh) {
                 for (int i = tid; i <= rows; i += THREADS) {
                     const int beg = (i == 0) ? 0 : s_re[i - 1] - y0;
                     const int end = (i == rows) ? nz : s_re[i] - y0;
-                    const V sum = row_sum<V>(a.x, pc, pv, beg, end);
+                    const V sum = row_sum<V, decltype(coh)::value>(a.x, pc, pv, beg, end);
                     V xr = 0;
                     if constexpr (DOT) {
                         // after the gathers: x[row] was just fetched for the diagonal entry (an L1 hit) and the
@@ -349,6 +409,8 @@ spmv_kernel(SpmvArgs<V> a, CgScalars cg)
                         s_tcarry[slot] = sum;
                     }
                 }
+                };
+                if (tile_halo) row_path(std::true_type{}); else row_path(std::false_type{});
             } else {
                 // ---- general tile, phase A: products in place -----------------------------------------
                 // Coalesced and branch-free: 16-byte groups of values and their columns are read with
@@ -374,7 +436,7 @@ spmv_kernel(SpmvArgs<V> a, CgScalars cg)
                                 c[0] = cc.x; c[1] = cc.y; c[2] = cc.z; c[3] = cc.w;
                             }
 #pragma unroll
-                            for (int e = 0; e < EPV; ++e) xv[q][e] = __ldg(a.x + c[e]);
+                            for (int e = 0; e < EPV; ++e) xv[q][e] = tile_halo ? gather<V, true>(a.x + c[e]) : gather<V, false>(a.x + c[e]);
                         }
                     }
 #pragma unroll
@@ -509,12 +571,34 @@ spmv_kernel(SpmvArgs<V> a, CgScalars cg)
 
     __syncthreads();   // all tiles done (producer warp included)
 
-    // ---- CTA carry-out ---------------------------------------------------------------------------
-    if (tid == 0) {
-        const bool any = t1 > t0;
-        a.carry_row[blockIdx.x] = any ? a.tile_xy[t1].x : a.m;
-        a.carry_val[blockIdx.x] = any ? s_running : V(0);
+    // ---- rows cut by the CTA boundaries: wait-free exchange through one slot per boundary --------
+    // (merge_based.hpp:137-149: the carry is added to what the row's owner stored.)  The dot product
+    // is linear in the parts of a row, so every CTA adds carry-out * x[row] to its own partial and no
+    // cross-CTA fix-up of p.Ap is needed.
+    V dot_carry = 0;
+    if (tid == 0 && t1 > t0 && !(a.debug_flags & 1)) {
+        const int c = blockIdx.x;
+        const int r0 = a.tile_xy[t0].x, r1 = a.tile_xy[t1].x;   // rows in progress at the start / end of this CTA
+        const bool has_in = c > 0 && r0 < a.m;
+        const V out = s_running;                                  // leading part of row r1 seen by this CTA
+        if constexpr (DOT) { if (r1 < a.m) dot_carry = out * __ldg(a.x + r1); }
+        __threadfence();   // this CTA's stores to y[r0] are ordered before its slot operations
+        if (r1 > r0) {
+            if (has_in) {  // this CTA owns the end of row r0: meet the carry of CTA c-1
+                const V mine = __ldcg(a.y + r0);
+                const V other = slot_exchange<V>(a.cta_slot + (c - 1), mine);
+                if (!is_sentinel<V>(other)) { slot_reset<V>(a.cta_slot + (c - 1)); a.y[r0] = mine + other; }
+            }
+            cta_carry_publish<V>(a.tile_xy, a.tiles_per_cta, a.num_tiles, a.m, a.cta_slot, a.y, c, out);
+        } else if (has_in) {   // the whole CTA lies inside row r0 == r1: pass the carry on
+            const V other = slot_exchange<V>(a.cta_slot + (c - 1), out);
+            if (!is_sentinel<V>(other)) { slot_reset<V>(a.cta_slot + (c - 1)); cta_carry_publish<V>(a.tile_xy, a.tiles_per_cta, a.num_tiles, a.m, a.cta_slot, a.y, c, other + out); }
+        } else {
+            cta_carry_publish<V>(a.tile_xy, a.tiles_per_cta, a.num_tiles, a.m, a.cta_slot, a.y, c, out);
+        }
     }
+
+    if constexpr (!DOT) return;
 
     if constexpr (DOT) {
 #pragma unroll
@@ -522,36 +606,20 @@ spmv_kernel(SpmvArgs<V> a, CgScalars cg)
         if (lane == 0 && warp < NW) s_wsum[warp] = dot;
         __syncthreads();
         if (tid == 0) {
-            V sdot = 0;
+            V sdot = dot_carry;
             for (int wi = 0; wi < NW; ++wi) sdot += s_wsum[wi];
             a.dot_part[blockIdx.x] = sdot;
         }
-    }
 
-    // ---- last CTA done: serial-order carry fix-up (merge_based.hpp:137-149) ----------------------
-    if (!last_cta_election(a.ticket, gridDim.x)) return;
-
-    const int entries = gridDim.x;
-    for (int e = tid; e < entries; e += blockDim.x) {
-        const int row = __ldcg(a.carry_row + e);
-        V fixdot = 0;
-        if (row < a.m && (e == 0 || __ldcg(a.carry_row + e - 1) != row)) {
-            V sum = 0;
-            for (int e2 = e; e2 < entries && __ldcg(a.carry_row + e2) == row; ++e2)
-                sum += __ldcg(a.carry_val + e2);
-            a.y[row] = __ldcg(a.y + row) + sum;
-            if constexpr (DOT) fixdot = sum * __ldg(a.x + row);
-        }
-        if constexpr (DOT) a.fix_part[e] = fixdot;
-    }
-    if constexpr (DOT) {
-        __syncthreads();
-        cta_reduce_columns<V>(a.dot_part, a.fix_part, entries, 1, (V *)cg.pAp, s_red);
+        // ---- last CTA done: p.Ap from the per-CTA partials in CTA order (deterministic) -------------
+        if (!last_cta_election(a.ticket, gridDim.x)) return;
+        const V pAp = cta_reduce_one<V>(a.dot_part, nullptr, gridDim.x, s_red);
+        if (tid == 0) cg.pAp[0] = (double)pAp;
         if (a.dist) {
-            // this rank's partial -> every peer's mailbox; K2 adds the G partials in rank order
-            if constexpr (sizeof(V) == 8) dist_post(*a.dist, 0, (double)cg.pAp[0], cg.ctrl);
+            // this rank's partial -> every rank's mailbox; K2 adds the G partials in rank order
+            dist_post(*a.dist, 0, (double)pAp, cg.ctrl);
         } else if (tid == 0) {
-            cg.alpha[0] = cg.conv[0] ? 0.0 : cg.rs_old[0] / cg.pAp[0];
+            cg.alpha[0] = cg.conv[0] ? 0.0 : cg.rs_old[0] / (double)pAp;
         }
     }
 }

@@ -17,13 +17,15 @@ There is NO CPU fallback: if the shared library is missing, or no CUDA device is
 every compute call raises SmleError.
 """
 from .capi import (SIMPLE, MERGE, NONZERO_SPLIT, CsrMatrix, SmleError, device_count, driver_threshold,
-                   gen_dense, gen_grid2d, gen_grid3d, gen_rhs_rand, gen_rmat, gen_wheel, get_stream,
+                   gen_dense, gen_grid2d, gen_grid3d, gen_grid3d_row_offsets, gen_grid3d_rows, gen_rhs_rand,
+                   gen_rhs_rand_range, gen_rmat, gen_wheel, get_stream, dist_bounds, host_register, host_unregister,
                    init, launch_count, lib, lib_path, merge_path_partition, set_stream, sm_count,
                    sync, DECLARED_SYMBOLS)
 
 __all__ = [
     "SIMPLE", "MERGE", "NONZERO_SPLIT", "CsrMatrix", "SmleError", "device_count", "driver_threshold",
-    "gen_dense", "gen_grid2d", "gen_grid3d", "gen_rhs_rand", "gen_rmat", "gen_wheel", "get_stream",
+    "gen_dense", "gen_grid2d", "gen_grid3d", "gen_grid3d_row_offsets", "gen_grid3d_rows", "gen_rhs_rand",
+    "gen_rhs_rand_range", "gen_rmat", "gen_wheel", "get_stream", "dist_bounds", "host_register", "host_unregister",
     "init", "launch_count", "lib", "lib_path", "merge_path_partition", "set_stream", "sm_count",
     "sync", "DECLARED_SYMBOLS",
 ]

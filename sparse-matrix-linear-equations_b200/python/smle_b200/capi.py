@@ -50,6 +50,7 @@ def lib():
         L.smle_get_stream.restype = _P
         L.smle_launch_count.restype = C.c_longlong
         L.smle_driver_threshold_f64.restype = _D
+        L.smle_dist_plan_request_size.restype = C.c_longlong
         _lib = L
     return _lib
 
@@ -321,6 +322,28 @@ def gen_grid3d(width, self_loop=True, diag=1.0, offd=1.0, dtype=np.float64):
     return _gen("grid3d", (_I(width), _I(int(self_loop))), (_I(width), _I(int(self_loop)), ct(diag), ct(offd)), dtype)
 
 
+def gen_grid3d_row_offsets(width, self_loop=True) -> np.ndarray:
+    """row offsets of InitGrid3d(width, self_loop) alone (m+1 ints): what a rank of the row-partitioned
+    solve needs to find its rows without building the matrix."""
+    m, n, nnz = _I(0), _I(0), _I(0)
+    _check(lib().smle_gen_grid3d_shape(_I(width), _I(int(self_loop)), C.byref(m), C.byref(n), C.byref(nnz)))
+    ro = np.empty(m.value + 1, dtype=np.int32)
+    _check(lib().smle_gen_grid3d_row_offsets(_I(width), _I(int(self_loop)), ro.ctypes.data_as(_P)))
+    return ro
+
+
+def gen_grid3d_rows(width, r0, r1, nnz_rows, self_loop=True, diag=1.0, offd=1.0):
+    """rows [r0, r1) of the same matrix: (local row offsets from 0, GLOBAL column indices, values);
+    nnz_rows = row_offsets[r1] - row_offsets[r0]."""
+    lro = np.empty(r1 - r0 + 1, dtype=np.int32)
+    ci = np.empty(nnz_rows, dtype=np.int32)
+    va = np.empty(nnz_rows, dtype=np.float64)
+    _check(lib().smle_gen_grid3d_rows_f64(_I(width), _I(int(self_loop)), _D(diag), _D(offd), _I(r0), _I(r1),
+                                          lro.ctypes.data_as(_P), ci.ctypes.data_as(_P), va.ctypes.data_as(_P)))
+    assert int(lro[-1]) == nnz_rows
+    return lro, ci, va
+
+
 def gen_wheel(spokes, value=1.0, dtype=np.float64):
     """InitWheel (sparse_matrix.h:417-450) -> CSR."""
     return _gen("wheel", (_I(spokes),), (_I(spokes), _ct(dtype)(value)), dtype)
@@ -342,6 +365,32 @@ def gen_rhs_rand(seed: int, count: int) -> np.ndarray:
     out = np.empty(count, dtype=np.float64)
     _check(lib().smle_gen_rhs_rand_f64(C.c_uint(seed), C.c_longlong(count), out.ctypes.data_as(_P)))
     return out
+
+
+def gen_rhs_rand_range(seed: int, first: int, count: int) -> np.ndarray:
+    """entries [first, first+count) of the srand(seed) stream (the values before are drawn and dropped)."""
+    out = np.empty(count, dtype=np.float64)
+    _check(lib().smle_gen_rhs_rand_range_f64(C.c_uint(seed), C.c_longlong(first), C.c_longlong(count),
+                                             out.ctypes.data_as(_P)))
+    return out
+
+
+def dist_bounds(row_offsets, world: int) -> np.ndarray:
+    """first row of every part of the row partition (world+1 ints): MergePathSearch on the share
+    diagonals g*ceil((m+nnz)/world), run on the GPU (smle_dist_bounds)."""
+    ro = np.ascontiguousarray(row_offsets, dtype=np.int32)
+    out = np.zeros(world + 1, dtype=np.int32)
+    _check(lib().smle_dist_bounds(ro.ctypes.data_as(_P), _I(len(ro) - 1), _I(world), out.ctypes.data_as(_P)))
+    return out
+
+
+def host_register(arr) -> None:
+    """page-lock a numpy array for overlapped copies (smle_host_register)."""
+    _check(lib().smle_host_register(_P(arr.ctypes.data), C.c_ulonglong(arr.nbytes)))
+
+
+def host_unregister(arr) -> None:
+    _check(lib().smle_host_unregister(_P(arr.ctypes.data)))
 
 
 def driver_threshold(b: np.ndarray, n: int, tol: float) -> float:

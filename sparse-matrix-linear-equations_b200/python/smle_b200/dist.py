@@ -10,8 +10,9 @@ Net-new relative to the reference (no distributed code there); SURVEY.md section
 * the halo index maps are exchanged once through torch.distributed (gloo or nccl -- plumbing
   only); the data path is the peer-memory kernels of csrc/smle_dist.cuh.
 
-Everything in the first half of this file is pure numpy and is exercised on CPU with a
-world_size-2 gloo group (tests/test_dist_host.py).
+The product path is the C planner behind the C ABI (csrc/smle_plan.cpp, `Plan` below): a rank hands
+in its own rows only.  The numpy functions in the first half restate the same plan; the CPU tests
+(tests/test_dist_host.py, world_size-2 gloo group) compare the two array for array.
 """
 from __future__ import annotations
 
@@ -34,6 +35,11 @@ def partition_rows(coords: np.ndarray, num_rows: int) -> np.ndarray:
     return rows
 
 
+def halo_base(n_local: int) -> int:
+    """first halo column of the local system: the halo tail starts on a 128-byte line of its own"""
+    return (n_local + 15) // 16 * 16
+
+
 def build_local_system(ro, ci, va, r0: int, r1: int):
     """rows [r0, r1) of the global CSR with columns remapped to [own | halo].
 
@@ -45,7 +51,7 @@ def build_local_system(ro, ci, va, r0: int, r1: int):
     own = (cols >= r0) & (cols < r1)
     halo_cols = np.unique(cols[~own])
     n_local = r1 - r0
-    lci = np.where(own, cols - r0, n_local + np.searchsorted(halo_cols, cols)).astype(np.int32)
+    lci = np.where(own, cols - r0, halo_base(n_local) + np.searchsorted(halo_cols, cols)).astype(np.int32)
     return lro, lci, np.ascontiguousarray(va[lo:hi]), halo_cols.astype(np.int64)
 
 
@@ -72,7 +78,7 @@ def send_plan(infos, rank: int, r0: int):
         want = np.asarray(infos[q]["need"].get(rank, np.zeros(0, np.int64)), dtype=np.int64) if q != rank else np.zeros(0, np.int64)
         idx.append((want - r0).astype(np.int32))
         send_off.append(send_off[-1] + len(want))
-        send_dst.append(int(infos[q]["n_local"] + infos[q]["recv_off"].get(rank, 0)))
+        send_dst.append(int(halo_base(infos[q]["n_local"]) + infos[q]["recv_off"].get(rank, 0)))
         needs_from.append(1 if q != rank and len(infos[rank]["need"].get(q, ())) > 0 else 0)
     send_idx = np.concatenate(idx) if idx else np.zeros(0, np.int32)
     return (np.asarray(send_off, np.int32), np.ascontiguousarray(send_idx, np.int32),
@@ -92,29 +98,97 @@ def make_plan(ro, ci, va, bounds, rank, all_gather_object):
 
 
 # ---------------------------------------------------------------------------------------------
+# the C planner (csrc/smle_plan.cpp) -- what the product uses; the numpy functions above restate it
+# for the CPU tests
+# ---------------------------------------------------------------------------------------------
+class Plan:
+    """smle_dist_plan_*: local system + push plan of one rank, from ITS rows only."""
+
+    def __init__(self, bounds, rank: int, world: int, n_global: int, lro, ci_global, all_gather_object=None):
+        """all_gather_object(bytes) -> list of every rank's bytes moves the request blobs; without it the
+        caller exchanges `request_blob()` itself and calls `finish(blobs)`."""
+        L = capi.lib()
+        self.bounds = np.ascontiguousarray(bounds, dtype=np.int32)
+        lro = np.ascontiguousarray(lro, dtype=np.int32)
+        ci_global = np.ascontiguousarray(ci_global, dtype=np.int32)
+        h = _P()
+        capi._check(L.smle_dist_plan_create(C.byref(h), _I(rank), _I(world), self.bounds.ctypes.data_as(_P), _I(n_global),
+                                            lro.ctypes.data_as(_P), ci_global.ctypes.data_as(_P)))
+        self._h = h
+        nl, nh, hb, nz = _I(0), _I(0), _I(0), _I(0)
+        capi._check(L.smle_dist_plan_dims(h, C.byref(nl), C.byref(nh), C.byref(hb), C.byref(nz)))
+        self.n_local, self.n_halo, self.halo_base, self.nnz_local = nl.value, nh.value, hb.value, nz.value
+        self.rank, self.world = rank, world
+        if all_gather_object is not None:
+            self.finish(all_gather_object(self.request_blob()))
+
+    def request_blob(self) -> bytes:
+        L = capi.lib()
+        blob = np.zeros(int(L.smle_dist_plan_request_size(self._h)), dtype=np.int32)
+        capi._check(L.smle_dist_plan_request(self._h, blob.ctypes.data_as(_P)))
+        return blob.tobytes()
+
+    def finish(self, blobs) -> None:
+        blobs = [np.frombuffer(b, dtype=np.int32) for b in blobs]
+        off = np.zeros(self.world + 1, dtype=np.int64)
+        off[1:] = np.cumsum([len(b) for b in blobs])
+        allb = np.ascontiguousarray(np.concatenate(blobs), dtype=np.int32)
+        capi._check(capi.lib().smle_dist_plan_finish(self._h, allb.ctypes.data_as(_P), off.ctypes.data_as(_P)))
+
+    def local_columns(self):
+        out = np.zeros(self.nnz_local, dtype=np.int32)
+        capi._check(capi.lib().smle_dist_plan_local_columns(self._h, out.ctypes.data_as(_P)))
+        return out
+
+    def halo_columns(self):
+        out = np.zeros(self.n_halo, dtype=np.int32)
+        capi._check(capi.lib().smle_dist_plan_halo_columns(self._h, out.ctypes.data_as(_P)))
+        return out
+
+    def send(self):
+        """(send_off, send_idx, send_dst, needs_from)"""
+        L = capi.lib()
+        so = np.zeros(self.world + 1, dtype=np.int32)
+        sd = np.zeros(self.world, dtype=np.int32)
+        nf = np.zeros(self.world, dtype=np.int32)
+        capi._check(L.smle_dist_plan_send(self._h, so.ctypes.data_as(_P), None, sd.ctypes.data_as(_P), nf.ctypes.data_as(_P)))
+        si = np.zeros(int(so[-1]), dtype=np.int32)
+        capi._check(L.smle_dist_plan_send(self._h, None, si.ctypes.data_as(_P), None, None))
+        return so, si, sd, nf
+
+    def close(self):
+        if getattr(self, "_h", None):
+            capi.lib().smle_dist_plan_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+# ---------------------------------------------------------------------------------------------
 # device side
 # ---------------------------------------------------------------------------------------------
 class RowPartitionedCsr:
-    """This rank's block of a row-partitioned CsrMatrix plus the NVLink peer connections."""
+    """This rank's block of a row-partitioned CsrMatrix plus the NVLink peer connections.
 
-    def __init__(self, ro, ci, va, rank: int, world: int, all_gather_object, bounds=None):
-        ro = np.ascontiguousarray(ro, dtype=np.int32)
-        m = len(ro) - 1
-        if bounds is None:
-            # merge-path coordinates on the GPU (bit-exact with the reference's MergePathSearch)
-            bounds = partition_rows(capi.merge_path_partition(ro, world), m)
-        self.bounds = np.asarray(bounds)
-        self.rank, self.world, self.num_rows_global = rank, world, m
-        p = make_plan(ro, ci, va, self.bounds, rank, all_gather_object)
-        self.plan = p
-        self.n_local = p["r1"] - p["r0"]
-        self.n_halo = len(p["halo_cols"])
-        self.local = capi.CsrMatrix(p["lro"], p["lci"], p["lva"], num_cols=self.n_local + self.n_halo)
+    The constructor takes the rank's OWN rows (local row offsets from 0, global column indices,
+    values) and the partition bounds; `from_global` slices them out of a global CSR, `grid3d`
+    generates the slab of InitGrid3d directly so that no rank ever holds the global matrix."""
+
+    def __init__(self, bounds, lro, ci_global, va, rank: int, world: int, all_gather_object):
+        self.bounds = np.asarray(bounds, dtype=np.int64)
+        self.rank, self.world = rank, world
+        self.num_rows_global = int(self.bounds[-1])
+        self.r0, self.r1 = int(self.bounds[rank]), int(self.bounds[rank + 1])
+        self.plan = Plan(bounds, rank, world, self.num_rows_global, lro, ci_global, all_gather_object)
+        self.n_local, self.n_halo = self.plan.n_local, self.plan.n_halo
         L = capi.lib()
+        va = np.ascontiguousarray(va, dtype=np.float64)
         h = _P()
-        capi._check(L.smle_dist_create(C.byref(h), self.local._h, _I(rank), _I(world), _I(self.n_local), _I(self.n_halo),
-                                       p["send_off"].ctypes.data_as(_P), p["send_idx"].ctypes.data_as(_P),
-                                       p["send_dst"].ctypes.data_as(_P), p["needs_from"].ctypes.data_as(_P)))
+        capi._check(L.smle_dist_create_from_plan(C.byref(h), self.plan._h, va.ctypes.data_as(_P)))
         self._h = h
         mine = (C.c_ubyte * 64)()
         capi._check(L.smle_dist_ipc_handle(self._h, mine))
@@ -122,11 +196,35 @@ class RowPartitionedCsr:
         blob = b"".join(handles)
         capi._check(L.smle_dist_connect(self._h, blob))
 
+    @classmethod
+    def from_global(cls, ro, ci, va, rank: int, world: int, all_gather_object, bounds=None):
+        ro = np.ascontiguousarray(ro, dtype=np.int32)
+        if bounds is None:
+            bounds = capi.dist_bounds(ro, world)   # merge-path search on the GPU, bit-exact with the reference
+        r0, r1 = int(bounds[rank]), int(bounds[rank + 1])
+        lo, hi = int(ro[r0]), int(ro[r1])
+        lro = (ro[r0:r1 + 1].astype(np.int64) - lo).astype(np.int32)
+        return cls(bounds, lro, ci[lo:hi], va[lo:hi], rank, world, all_gather_object)
+
+    @classmethod
+    def grid3d(cls, width: int, rank: int, world: int, all_gather_object, diag=6.0, offd=-1.0):
+        """3-D Poisson slab of this rank: global row offsets (4 B per row) -> bounds -> rows [r0, r1) only."""
+        ro = capi.gen_grid3d_row_offsets(width, True)
+        bounds = capi.dist_bounds(ro, world)
+        r0, r1 = int(bounds[rank]), int(bounds[rank + 1])
+        nnz_rows = int(ro[r1]) - int(ro[r0])
+        nnz_global = int(ro[-1])
+        del ro
+        lro, ci, va = capi.gen_grid3d_rows(width, r0, r1, nnz_rows, True, diag, offd)
+        self = cls(bounds, lro, ci, va, rank, world, all_gather_object)
+        self.num_nonzeros_global = nnz_global
+        return self
+
     def close(self):
         if getattr(self, "_h", None):
             capi.lib().smle_dist_destroy(self._h)
             self._h = None
-            self.local.close()
+            self.plan.close()
 
     def spmv(self, x_local, out=None):
         """y_local = (A x)_local; collective (call it on every rank, barrier between calls)."""
@@ -139,11 +237,13 @@ class RowPartitionedCsr:
         return y
 
     def cg_solve_single(self, b_local, max_iters: int, tolerance: float, out=None):
-        """-> (iterations, x_local, final_rel_res); CGSolveSingle semantics on the global system."""
-        import torch
-        x = out if out is not None else torch.empty(self.n_local, dtype=torch.float64, device=b_local.device)
-        pb, _, _ = capi._arg(b_local, np.float64)
-        px, _, _ = capi._arg(x, np.float64, writable=True)
+        """-> (iterations, x_local, final_rel_res); CGSolveSingle semantics on the global system.
+        b_local / out: this rank's rows, torch CUDA tensors (device) or numpy / pinned CPU tensors (host)."""
+        pb, dev, _ = capi._arg(b_local, np.float64)
+        x = out if out is not None else capi._empty_like_arg(b_local, (self.n_local,), np.float64)
+        px, dev_x, _ = capi._arg(x, np.float64, writable=True)
+        if dev != dev_x:
+            raise capi.SmleError("b and x must both be host or both be device memory")
         it, rel = _I(0), _D(0)
-        capi._check(capi.lib().smle_dist_cg_f64(self._h, pb, px, _I(max_iters), _D(tolerance), C.byref(it), C.byref(rel)))
+        capi._check(capi.lib().smle_dist_cg_f64(self._h, pb, px, _I(max_iters), _D(tolerance), _I(dev), C.byref(it), C.byref(rel)))
         return it.value, x, rel.value

@@ -1,6 +1,6 @@
 """GPU (needs >= 2 devices): row-partitioned SpMV and CG over NVLink peer memory against the
-oracle on the global system.  One process per GPU; torch.distributed (gloo) only moves the halo
-index maps and the CUDA IPC handles."""
+oracle on the global system.  One process per GPU; torch.distributed (gloo) only moves the request
+blobs of the planner and the CUDA IPC handles."""
 import os
 import sys
 from pathlib import Path
@@ -12,7 +12,18 @@ pytestmark = pytest.mark.gpu
 ROOT = Path(__file__).resolve().parents[1]
 
 
-def _worker(rank, world, port, w, q):
+def _spd_random(m, seed):
+    """diagonally dominant symmetric matrix with a scattered pattern: halo columns everywhere, send
+    lists that are not contiguous runs (the separate push kernel is chosen automatically)"""
+    import scipy.sparse as sp
+    W = sp.random(m, m, density=6.0 / m, random_state=np.random.RandomState(seed), format="csr")
+    W = W + W.T
+    A = (sp.diags(np.asarray(W.sum(axis=1)).ravel() + 1.0) - W).tocsr()
+    A.sort_indices()
+    return A.indptr.astype(np.int32), A.indices.astype(np.int32), A.data.astype(np.float64)
+
+
+def _worker(rank, world, port, kind, q):
     sys.path.insert(0, str(ROOT))
     sys.path.insert(0, str(ROOT / "sparse-matrix-linear-equations_b200" / "python"))
     import torch
@@ -32,10 +43,17 @@ def _worker(rank, world, port, w, q):
         return out
 
     orc = O.port()
-    ro, ci, va = S.gen_grid3d(w, True, 6.0, -1.0)
+    w = 40
+    if kind == "random":
+        ro, ci, va = _spd_random(30000, 5)
+    else:
+        ro, ci, va = S.gen_grid3d(w, True, 6.0, -1.0)
     m = len(ro) - 1
-    A = D.RowPartitionedCsr(ro, ci, va, rank, world, gather)
-    r0, r1 = A.plan["r0"], A.plan["r1"]
+    if kind == "slab":
+        A = D.RowPartitionedCsr.grid3d(w, rank, world, gather)          # this rank generates its rows only
+    else:
+        A = D.RowPartitionedCsr.from_global(ro, ci, va, rank, world, gather)
+    r0, r1 = A.r0, A.r1
     bounds_ok = np.array_equal(A.bounds, D.partition_rows(orc.merge_partition(ro, world), m))
 
     x = np.cos(np.arange(m) * 0.37)
@@ -45,21 +63,31 @@ def _worker(rank, world, port, w, q):
     dist.barrier()
 
     b = S.gen_rhs_rand(42, m)
+    assert np.array_equal(S.gen_rhs_rand_range(42, r0, r1 - r0), b[r0:r1])
     res = []
-    for tol in (1e-5, 1e-9):
-        it, xs, rel = A.cg_solve_single(torch.from_numpy(b[r0:r1].copy()).cuda(), 10000, tol)
+    for tol, host in ((1e-5, False), (1e-9, False), (1e-7, True)):
+        if host:   # host buffers through the C ABI (is_device_ptr = 0)
+            it, xs, rel = A.cg_solve_single(b[r0:r1].copy(), 10000, tol)
+        else:
+            it, xs, rel = A.cg_solve_single(torch.from_numpy(b[r0:r1].copy()).cuda(), 10000, tol)
+            xs = xs.cpu().numpy()
         it_ref, x_ref = orc.cg_single(ro, ci, va, b, 10000, tol)
-        err = float(np.abs(xs.cpu().numpy() - x_ref[r0:r1]).max() / np.abs(x_ref).max())
+        err = float(np.abs(xs - x_ref[r0:r1]).max() / np.abs(x_ref).max())
         res.append((it, it_ref, err, rel))
         dist.barrier()
+    # max_iters cap: every rank stops after exactly 7 iterations
+    it, _, _ = A.cg_solve_single(torch.from_numpy(b[r0:r1].copy()).cuda(), 7, 1e-30)
+    res.append((it, 7, 0.0, 0.0))
+    dist.barrier()
     q.put((rank, bounds_ok, spmv_err, res))
     A.close()
     dist.barrier()
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,fused", [(2, 1), (2, 0), (4, 1), (8, 1)])
-def test_row_partitioned_spmv_and_cg(gpu, world, fused, monkeypatch):
+@pytest.mark.parametrize("world,kind,fused", [(2, "global", 1), (2, "global", 0), (2, "slab", 1), (2, "random", 1),
+                                              (4, "slab", 1), (4, "random", 1), (8, "slab", 1), (8, "global", 0)])
+def test_row_partitioned_spmv_and_cg(gpu, world, kind, fused, monkeypatch):
     """fused = 1: K3 stores the boundary rows of the new p straight into the neighbours' halo tails;
     fused = 0: the separate halo push kernel (the path matrices with scattered send lists take)."""
     if gpu.device_count() < world:
@@ -68,18 +96,42 @@ def test_row_partitioned_spmv_and_cg(gpu, world, fused, monkeypatch):
     monkeypatch.setenv("SMLE_DIST_FUSED_PUSH", str(fused))
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    procs = [ctx.Process(target=_worker, args=(r, world, 29700 + 10 * world + fused, 40, q)) for r in range(world)]
+    port = 29700 + 10 * world + fused + 2 * ["global", "slab", "random"].index(kind)
+    procs = [ctx.Process(target=_worker, args=(r, world, port, kind, q)) for r in range(world)]
     for p in procs:
         p.start()
-    res = sorted(q.get(timeout=300) for _ in range(world))
-    for p in procs:
-        p.join(timeout=60)
-        assert p.exitcode == 0
+    try:
+        res = sorted(q.get(timeout=300) for _ in range(world))
+    finally:
+        for p in procs:
+            p.join(timeout=60)
+            if p.is_alive():
+                p.kill()
+    assert all(p.exitcode == 0 for p in procs)
     for rank, bounds_ok, spmv_err, cg in res:
         assert bounds_ok, "partition rows differ from the reference merge-path search"
         assert spmv_err <= 1e-12
         for it, it_ref, err, rel in cg:
             assert abs(it - it_ref) <= max(1, round(0.02 * it_ref)), (it, it_ref)
             assert err <= 1e-6
-    # every rank must report the same iteration count
+    # every rank must report the same iteration counts
     assert len({tuple(c[0] for c in r[3]) for r in res}) == 1
+
+
+def test_world1_partition_is_the_plain_solver(gpu, orc):
+    """a partition of one rank goes through the same kernels (mailbox to itself, no halo)"""
+    import torch
+    from smle_b200 import dist as D
+    A = D.RowPartitionedCsr.grid3d(24, 0, 1, lambda obj: [obj])
+    ro, ci, va = gpu.gen_grid3d(24, True, 6.0, -1.0)
+    n = len(ro) - 1
+    assert A.n_local == n and A.n_halo == 0
+    b = gpu.gen_rhs_rand(42, n)
+    it, x, rel = A.cg_solve_single(torch.from_numpy(b).cuda(), 10000, 1e-8)
+    it_ref, x_ref = orc.cg_single(ro, ci, va, b, 10000, 1e-8)
+    assert abs(it - it_ref) <= max(1, round(0.02 * it_ref))
+    assert np.abs(x.cpu().numpy() - x_ref).max() <= 1e-6 * np.abs(x_ref).max()
+    # host buffers
+    it2, x2, _ = A.cg_solve_single(b, 10000, 1e-8)
+    assert it2 == it and np.array_equal(x2, x.cpu().numpy())
+    A.close()
