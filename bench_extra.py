@@ -162,8 +162,9 @@ def run_stress(args):
 
 
 def run_rowcg(args):
-    """configs[4]: row-partitioned fp64 CG on 3-D Poisson 300^3, halo push + mailbox all-reduce over
-    NVLink peer memory; strong scaling (fixed global problem)."""
+    """configs[4] with a FIXED iteration count (no convergence exit): per-iteration time and the
+    per-kernel timeline (K1 / K2 / K3 including their waits for the peers) of the row-partitioned CG.
+    The driver's line is bench.py's default workload; this is the builder's breakdown of it."""
     import time
     import torch.distributed as dist
     torch, S, st = _setup()
@@ -172,7 +173,7 @@ def run_rowcg(args):
     rank = int(os.environ.get("RANK", "0"))
     os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
     os.environ.setdefault("MASTER_PORT", "29533")
-    dist.init_process_group("gloo", rank=rank, world_size=world)   # plumbing only (index maps, IPC handles)
+    dist.init_process_group("gloo", rank=rank, world_size=world)   # plumbing only (request blobs, IPC handles)
 
     def gather(obj):
         out = [None] * world
@@ -182,14 +183,9 @@ def run_rowcg(args):
     w = int(os.environ.get("SMLE_ROWCG_GRID", "300"))
     iters = int(os.environ.get("SMLE_ROWCG_ITERS", "400"))
     t0 = time.time()
-    ro, ci, va = S.gen_grid3d(w, True, 6.0, -1.0)
-    m, nnz = len(ro) - 1, len(ci)
-    A = D.RowPartitionedCsr(ro, ci, va, rank, world, gather)
-    r0, r1 = A.plan["r0"], A.plan["r1"]
-    del ro, ci, va
-    # b from the srand(42) stream would need 27M rand() calls per rank; a smooth deterministic RHS is
-    # enough for a fixed-iteration-count timing run
-    b = torch.cos(torch.arange(r0, r1, dtype=torch.float64, device="cuda") * 0.001) + 1.5
+    A = D.RowPartitionedCsr.grid3d(w, rank, world, gather)
+    m, nnz = A.num_rows_global, A.num_nonzeros_global
+    b = torch.from_numpy(S.gen_rhs_rand_range(42, A.r0, A.n_local)).cuda()
     x = torch.empty_like(b)
     setup_s = time.time() - t0
     with torch.cuda.stream(st):
@@ -202,15 +198,18 @@ def run_rowcg(args):
         e1.record(st)
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1)
-    allms = gather(ms)
+        dist.barrier()
+        kms = A.cg_profile(b, 40)
+    allms = gather((ms, kms))
     if rank == 0:
-        ms = max(allms)
+        ms = max(a[0] for a in allms)
         per_iter = ms / it
         bytes_iter = nnz * 12 + (m + 1) * 4 + 11 * m * 8
         print(json.dumps({"workload": f"row-partitioned CG fp64 3-D Poisson {w}^3 ({m} rows, {nnz} nnz) over {world} GPU(s)",
                           "iterations": it, "ms_per_iteration": per_iter, "iterations_per_s": 1e3 / per_iter,
                           "aggregate_algorithmic_GBs": bytes_iter / per_iter / 1e6,
                           "frac_of_measured_hbm_per_gpu": bytes_iter / per_iter / 1e6 / world / _peak(),
+                          "kernel_us_per_rank_ungraphed": [[round(1e3 * v, 1) for v in a[1]] for a in allms],
                           "halo_entries_this_rank": A.n_halo, "rows_per_rank": [int(v) for v in np.diff(A.bounds)],
                           "final_rel_res": rel, "setup_s": setup_s, "scaling": "strong"}), flush=True)
     dist.barrier()

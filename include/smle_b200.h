@@ -199,6 +199,8 @@ int smle_dist_dims(smle_dist_t d, int *n_local, int *n_halo, int *rank, int *wor
 int smle_dist_spmv_f64(smle_dist_t d, const double *x_local_dev, double *y_local_dev);
 int smle_dist_cg_f64(smle_dist_t d, const double *b_local, double *x_local, int max_iters, double tol,
                      int is_device_ptr, int *iters_out, double *final_rel_res);
+/* per-kernel timing of the row-partitioned iteration, like smle_cg_profile_f64 (collective) */
+int smle_dist_cg_profile_f64(smle_dist_t d, const double *b_local_dev, int iters, float *ms_per_kernel);
 void smle_dist_destroy(smle_dist_t d);
 
 /* ---- matrix / RHS generators (host side) -------------------------------------------------

@@ -216,6 +216,15 @@ class _Backend:
                                               _ptr(ro), _ptr(ci), _ptr(va))
         return ro, ci, va
 
+    def gen_grid3d_sorted(self, w, self_loop=True, diag=1.0, offd=1.0, dtype=np.float64):
+        """the CSR of gen_grid3d built directly in sorted order (port only; for the 300^3 bench system)"""
+        s, ct = _sfx(dtype), _ct(dtype)
+        m, _, nnz = self._shape("gen_grid3d_shape", w, int(self_loop))
+        ro, ci, va = self._alloc(m, nnz, dtype)
+        self._f(self._cg, f"gen_grid3d_sorted_{s}")(_I(w), _I(int(self_loop)), ct(diag), ct(offd),
+                                                     _ptr(ro), _ptr(ci), _ptr(va))
+        return ro, ci, va
+
     def gen_wheel(self, spokes, value=1.0, dtype=np.float64):
         s, ct = _sfx(dtype), _ct(dtype)
         ro, ci, va = self._alloc(spokes + 1, 2 * spokes, dtype)

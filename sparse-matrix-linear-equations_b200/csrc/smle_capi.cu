@@ -1544,4 +1544,64 @@ int smle_dist_cg_f64(smle_dist_t d, const double *b_local, double *x_local, int 
     return SMLE_OK;
 }
 
+// Per-kernel timing of the row-partitioned iteration (roofline report): `iters` iterations WITHOUT
+// the CUDA graph, CUDA events around K1 (local SpMV + p.Ap post), K2, K3 (+ halo push).  The waits
+// for the peers are inside the kernels, so their cost shows up in the kernel that waits.  Collective.
+int smle_dist_cg_profile_f64(smle_dist_t d, const double *b_local_dev, int iters, float *ms_per_kernel)
+{
+    if (!d || !b_local_dev || iters < 1 || !ms_per_kernel) return fail(SMLE_ERR_ARG, "bad argument");
+    if (!d->connected) return fail(SMLE_ERR_COMM, "smle_dist_connect has not been called");
+    smle_csr_t a = d->a;
+    int rc = ensure_workspace(a, 1, 0);
+    if (!rc) rc = ensure_scratch(a, 1);
+    if (rc) return rc;
+    CgWorkspace &w = a->ws;
+    CgScalars cg = make_scalars(w, 1);
+    CgVecArgs va;
+    va.B = b_local_dev; va.X = w.Xd; va.R = w.R; va.P = dist_p(d); va.AP = w.AP;
+    va.n = d->n_local; va.k = 1; va.part = w.part; va.ticket = a->ticket + 1;
+    rc = launch_merge<double, true>(a, va.P, va.AP, 1, cg, /*dry=*/true);
+    if (!rc) rc = launch_vec(0, va, cg, iters + 2, -1.0, d->seq_base);
+    if (rc) return rc;
+    dist_post_kernel<<<1, 32, 0, g_stream>>>(d->ctl, 2, cg.rs_old, cg.ctrl);
+    cg1d_update_xp_kernel<<<1, kThreads, 0, g_stream>>>(va, cg, d->ctl, 1);
+    dist_halo_push_kernel<<<dist_push_grid(d), kThreads, 0, g_stream>>>(d->ctl, va.P, cg.ctrl);
+    g_launches += 3;
+    rc = check_launch("distributed CG init");
+    if (rc) return rc;
+    std::vector<cudaEvent_t> ev((size_t)iters * 4);
+    for (auto &e : ev) CU(cudaEventCreate(&e));
+    const int grid = dist_vec_grid(va.n);
+    rc = dist_launch_iteration(d, va, cg);   // warm-up iteration, untimed
+    for (int i = 0; i < iters && !rc; ++i) {
+        CU(cudaEventRecord(ev[(size_t)i * 4 + 0], g_stream));
+        g_spmv_dist = d->ctl_dev;
+        rc = launch_merge<double, true>(a, va.P, va.AP, 1, cg);
+        g_spmv_dist = nullptr;
+        CU(cudaEventRecord(ev[(size_t)i * 4 + 1], g_stream));
+        cg1d_update_r_kernel<<<grid, kThreads, 0, g_stream>>>(va, cg, d->ctl);
+        CU(cudaEventRecord(ev[(size_t)i * 4 + 2], g_stream));
+        cg1d_update_xp_kernel<<<grid, kThreads, 0, g_stream>>>(va, cg, d->ctl, 0);
+        if (!d->ctl.fused) dist_halo_push_kernel<<<dist_push_grid(d), kThreads, 0, g_stream>>>(d->ctl, va.P, cg.ctrl);
+        CU(cudaEventRecord(ev[(size_t)i * 4 + 3], g_stream));
+        g_launches += d->ctl.fused ? 2 : 3;
+        if (!rc) rc = check_launch("distributed CG iteration");
+    }
+    cudaError_t e = cudaStreamSynchronize(g_stream);
+    if (!rc && e != cudaSuccess) rc = fail(SMLE_ERR_CUDA, "sync failed: %s", cudaGetErrorString(e));
+    double acc[3] = {0, 0, 0};
+    if (!rc) {
+        for (int i = 0; i < iters; ++i)
+            for (int j = 0; j < 3; ++j) {
+                float ms = 0.f;
+                cudaEventElapsedTime(&ms, ev[(size_t)i * 4 + j], ev[(size_t)i * 4 + j + 1]);
+                acc[j] += ms;
+            }
+        for (int j = 0; j < 3; ++j) ms_per_kernel[j] = (float)(acc[j] / iters);
+    }
+    for (auto &ev1 : ev) cudaEventDestroy(ev1);
+    d->seq_base += iters + 4;   // iterations run (incl. the warm-up) + margin
+    return rc;
+}
+
 } // extern "C"

@@ -121,6 +121,27 @@ cg_init_kernel(CgVecArgs a, CgScalars cg, int max_iters, double tol, int seq_bas
 __device__ __forceinline__ void cg_finalize_r(const CgVecArgs &a, const CgScalars &cg, double *s_red, int *s_cnt)
 {
     const int tid = threadIdx.x;
+    if (a.k == 1) {
+        // single right-hand side: shuffle-tree reduction, bookkeeping by one thread (the generic path
+        // below spends ~3 us of every iteration in block-wide trees over a single value)
+        const double rn = cta_reduce_one<double>(a.part, nullptr, gridDim.x, s_red);
+        if (tid == 0) {
+            const double ro = cg.rs_old[0];
+            const double rel = sqrt(rn) / cg.bnorm[0];
+            int cv = cg.conv[0];
+            if (!cv && rel < *cg.tol) { cv = 1; cg.conv[0] = 1; }
+            cg.rs_new[0] = rn;
+            cg.beta[0] = cv ? 0.0 : rn / ro;
+            cg.rs_old[0] = rn;
+            const int it = cg.ctrl[CTRL_ITER];
+            if (cg.hist && it < cg.hist_cap) cg.hist[it] = rel;
+            *cg.last_rel = rel;
+            cg.ctrl[CTRL_ITER] = it + 1;
+            cg.ctrl[CTRL_NCONV] = cv;
+            if (cv || it + 1 >= cg.ctrl[CTRL_MAX_ITERS]) cg.ctrl[CTRL_STOP] = 1;
+        }
+        return;
+    }
     cta_reduce_columns<double>(a.part, nullptr, gridDim.x, a.k, cg.rs_new, s_red);
 
     double worst = 0.0;

@@ -247,3 +247,12 @@ class RowPartitionedCsr:
         it, rel = _I(0), _D(0)
         capi._check(capi.lib().smle_dist_cg_f64(self._h, pb, px, _I(max_iters), _D(tolerance), _I(dev), C.byref(it), C.byref(rel)))
         return it.value, x, rel.value
+
+    def cg_profile(self, b_local, iters: int):
+        """mean ms of the three kernels of a row-partitioned iteration (CUDA events, no graph); collective"""
+        pb, dev, _ = capi._arg(b_local, np.float64)
+        if not dev:
+            raise capi.SmleError("cg_profile needs a device tensor")
+        out = (C.c_float * 3)()
+        capi._check(capi.lib().smle_dist_cg_profile_f64(self._h, pb, _I(iters), out))
+        return [float(v) for v in out]
