@@ -353,7 +353,7 @@ spmv_kernel(SpmvArgs<V> a, CgScalars cg)
         // tile metadata is fetched one tile ahead so its latency hides behind the previous tile
         int2 nxt_lo = make_int2(0, 0), nxt_hi = make_int2(0, 0);
         int nxt_ml = 0;
-        bool nxt_halo = false;
+        bool nxt_halo = false, halo_ready = false;
         if (t0 < t1) {
             nxt_lo = a.tile_xy[t0]; nxt_hi = a.tile_xy[t0 + 1]; nxt_ml = a.tile_maxlen[t0];
             if (a.tile_halo) nxt_halo = a.tile_halo[t0] != 0;
@@ -381,9 +381,10 @@ spmv_kernel(SpmvArgs<V> a, CgScalars cg)
             if (tid == 0) s_trow[slot] = rows > 0 ? x0 : -1;
 
             mbar_wait(&s_full[s], parity);
-            // row-partitioned solve: only the tiles that gather halo columns wait for the neighbours'
-            // push of this iteration's p; interior tiles never look at the flags
-            if (tile_halo) dist_wait_halo(*a.dist, cg.ctrl);
+            // row-partitioned solve: only tiles that gather halo columns wait for the neighbours' push of
+            // this iteration's p, and a warp waits ONCE per launch (the sys-scope acquire invalidates L1:
+            // per tile it cost 100 us on the CTAs that own the boundary); interior tiles never look
+            if (tile_halo && !halo_ready) { dist_wait_halo(*a.dist, cg.ctrl); halo_ready = true; }
 
             if (a.debug_flags & 1) {
                 // measurement aid: stream the tile through shared memory and do nothing with it

@@ -78,3 +78,64 @@ def test_mtx_roundtrip_through_gpu_driver(gpu, tmp_path):
     _run("mtx_tool", "--grid2d=30", "--poisson", f"--out={tmp_path}/g.mtx")
     out = _run("gpu_spmv", f"--mtx={tmp_path}/g.mtx", "--i=5")
     assert "PASS" in out
+
+
+def test_gpu_multicg_sweep_is_the_missing_cpu_multicg2(gpu, orc, tmp_path):
+    """`gpu_multicg --sweep` = the cpu_multicg2 the reference's Makefile:191 names but does not ship:
+    invoked as eval_gflops.sh:61-66 does (--mtx --output --threads --timing_iters --quiet), it must
+    write the CSV verification/gflops/gflop_analyze.py:13-52 consumes (pivot kernel x num_vectors of
+    "gflops(iterations)") and the three SpmmKernel values must all reproduce CGSolveMultiple."""
+    import pandas as pd
+    _run("mtx_tool", "--grid3d=12", "--poisson", f"--out={tmp_path}/p12.mtx")
+    csv_path = tmp_path / "p12_gflops.csv"
+    _run("gpu_multicg", f"--mtx={tmp_path}/p12.mtx", f"--output={csv_path}", "--threads=17", "--timing_iters=1", "--quiet", "--sweep")
+    lines = csv_path.read_text().splitlines()
+    assert lines[0] == "matrix_name,kernel,num_vectors,min_ms,gflops,iterations"
+    df = pd.read_csv(csv_path)
+    assert len(df) == 21 and set(df["kernel"]) == {"SIMPLE", "MERGE", "NONZERO_SPLIT"}
+    assert sorted(set(df["num_vectors"])) == [2, 4, 8, 16, 32, 64, 128]      # cpu_singlecg.cpp:159
+    assert (df["matrix_name"] == "p12").all() and (df["gflops"] > 0).all() and (df["min_ms"] > 0).all()
+    # the analysis script's own steps (gflop_analyze.py:27-52)
+    df["formatted_value"] = df["gflops"].astype(str) + "(" + df["iterations"].astype(str) + ")"
+    for kernel in df["kernel"].unique():
+        piv = df[df["kernel"] == kernel].pivot_table(index="matrix_name", columns="num_vectors", values="formatted_value", aggfunc="first")
+        piv = piv.reindex(sorted(piv.columns), axis=1)
+        assert piv.shape == (1, 7) and not piv.isna().any().any()
+    # iteration counts: each (kernel, k) against the oracle's CGSolveMultiple with that SpmmKernel
+    ro, ci, va = orc.gen_grid3d(12, True, 6.0, -1.0)
+    n = len(ro) - 1
+    for kname, kid in (("SIMPLE", O.SIMPLE), ("MERGE", O.MERGE), ("NONZERO_SPLIT", O.NONZERO_SPLIT)):
+        for k in (2, 16, 128):
+            B = orc.rhs_rand(42, n * k).reshape(n, k)
+            thr = orc.driver_threshold(B.ravel(), n, 1e-5)
+            want = orc.cg_multi(ro, ci, va, B, k, 50000, thr, kid, 8)[0]
+            got = int(df[(df["kernel"] == kname) & (df["num_vectors"] == k)]["iterations"].iloc[0])
+            assert abs(got - want) <= max(1, round(0.02 * want)), (kname, k, got, want)
+
+
+def test_gpu_singlecg_row_partitioned_over_two_gpus(gpu, orc, tmp_path):
+    """--gpus=2: one forked worker per GPU, planner and IPC handles through shared memory
+    (host/smle_multi.hpp); same totals as the single-GPU driver and as the oracle."""
+    if gpu.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    out = _run("gpu_singlecg", "--grid3d=24", "--num_vectors=3", "--gpus=2", "--check", f"--output={tmp_path}/r2.csv")
+    m = re.search(r"method=SINGLE_LOOP: [\d.]+ ms, (\d+) iters", out)
+    assert m, out
+    total = int(m.group(1))
+    ro, ci, va = orc.gen_grid3d(24, True, 6.0, -1.0)
+    n = len(ro) - 1
+    b = orc.rhs_rand(42, n * 3)
+    thr = orc.driver_threshold(b, n, 1e-5)
+    want = sum(orc.cg_single(ro, ci, va, b[v * n:(v + 1) * n].copy(), 10000, thr)[0] for v in range(3))
+    assert abs(total - want) <= max(1, round(0.02 * want))
+    assert "row partition over 2 GPU(s): [0,6912) halo 576 [6912,13824) halo 576" in out     # merge-path cut, one 24x24 plane each
+    res = float(re.search(r"true residual of vector 0: ([\d.e+-]+)", out).group(1))
+    assert res < thr * 1.01
+    assert (tmp_path / "r2.csv").read_text().splitlines()[1].startswith("grid3d_24,SINGLE_LOOP,3,")
+
+
+def test_gpu_singlecg_partitioned_flag_on_one_gpu(gpu, tmp_path):
+    """--partitioned with one GPU goes through the same forked-worker path (world = 1)"""
+    out = _run("gpu_singlecg", "--grid3d=16", "--num_vectors=2", "--partitioned", "--check", f"--output={tmp_path}/r1.csv")
+    assert "row partition over 1 GPU(s): [0,4096) halo 0" in out
+    assert re.search(r"method=SINGLE_LOOP: [\d.]+ ms, (\d+) iters", out)
