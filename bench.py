@@ -25,6 +25,7 @@ Other workloads (builder measurements of the remaining configs; not the driver's
     --workload spmv     configs[0] merge-path SpMV, grid2d 1000^2 (+ the cold-cache rotation)
     --workload multicg  configs[2] multi-RHS CG k=32 on 200^3, columns sharded over ranks
     --workload stress   configs[3] RMAT / wheel SpMV & SpMM sweep
+    --workload rowcg_fixed  configs[4] with a fixed iteration count + the per-rank kernel timeline
 
 `roofline`: dominant kernel = the TMA-staged merge-path SpMV + p.Ap (spmv_kernel<DOT>) on the rank's
 slab, algorithmic bytes / CUDA-event time against MEASURED_PEAKS.json.  `cpu_baseline` / `--impl

@@ -218,4 +218,4 @@ def run_rowcg(args):
 
 
 def run(args):
-    return {"spmv": run_spmv, "multicg": run_multicg, "stress": run_stress, "rowcg": run_rowcg}[args.workload](args)
+    return {"spmv": run_spmv, "multicg": run_multicg, "stress": run_stress, "rowcg_fixed": run_rowcg}[args.workload](args)

@@ -12,6 +12,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 
+#include <algorithm>
 #include <map>
 #include <new>
 #include <vector>
@@ -140,6 +141,9 @@ struct Partition {
     int *maxlen = nullptr; // device, num_tiles: longest in-tile row segment
     int max_len = 0;       // max over maxlen[] (host copy): picks the SpMM kernel
     unsigned char *halo = nullptr;   // device, num_tiles: tile gathers halo columns (row-partitioned handles only)
+    // structure-aware SpMM tile schedules, keyed by grid size (smle_spmm.cuh); sched == nullptr: none
+    struct Sched { int *sched = nullptr, *off = nullptr; };
+    std::map<int, Sched> scheds;
 };
 
 struct smle_csr_s {
@@ -160,6 +164,7 @@ struct smle_csr_s {
     // graphs captured under an older epoch are rebuilt before their next launch.
     unsigned scratch_epoch = 0;
     int halo_base = -1;               // local block of a row partition: first halo column (else -1)
+    int far_stride = -1;              // dominant far column offset in rows (0: none, -1: not probed yet)
     CgWorkspace ws;
 };
 
@@ -339,6 +344,122 @@ int env_int(const char *name, int dflt)
     return e ? atoi(e) : dflt;
 }
 
+// ---- structure-aware tile schedule of the row-per-worker SpMM kernel --------------------------------
+// far_stride: the largest column offset D > 0 that at least 40 % of a sample of rows have a nonzero
+// at (the w^2 plane offset of a 3-D stencil); 0 when there is none (R-MAT, wheel, 2-D grids whose far
+// offset is within a tile or two).
+int far_stride(smle_csr_t a, int *out)
+{
+    if (a->far_stride >= 0) { *out = a->far_stride; return SMLE_OK; }
+    a->far_stride = 0;
+    *out = 0;
+    if (a->m < 4096 || a->m != a->n) return SMLE_OK;
+    const int ns = 2048;
+    int *d_out = nullptr;
+    CU(cudaMalloc(&d_out, sizeof(int) * ns * kSampleNnz));
+    sample_offsets_kernel<<<(ns + 127) / 128, 128, 0, g_stream>>>(a->ro, a->ci, a->m, ns, d_out);
+    ++g_launches;
+    std::vector<int> h((size_t)ns * kSampleNnz);
+    cudaError_t e = cudaMemcpyAsync(h.data(), d_out, sizeof(int) * h.size(), cudaMemcpyDeviceToHost, g_stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(g_stream);
+    cudaFree(d_out);
+    if (e != cudaSuccess) return fail(SMLE_ERR_CUDA, "structure probe failed: %s", cudaGetErrorString(e));
+    std::map<int, int> freq;   // offset -> rows of the sample that have it
+    for (int i = 0; i < ns; ++i) {
+        int seen[kSampleNnz], nseen = 0;
+        for (int j = 0; j < kSampleNnz; ++j) {
+            const int o = h[(size_t)i * kSampleNnz + j];
+            if (o == INT_MIN || o <= 0) continue;
+            bool dup = false;
+            for (int q = 0; q < nseen; ++q) dup |= seen[q] == o;
+            if (!dup) { seen[nseen++] = o; ++freq[o]; }
+        }
+    }
+    for (auto it = freq.rbegin(); it != freq.rend(); ++it)
+        if (it->second * 10 >= ns * 4) { a->far_stride = it->first; break; }
+    *out = a->far_stride;
+    return SMLE_OK;
+}
+
+// Chains of tiles D rows apart, cut into segments, dealt round-robin in order of their first tile.
+int get_tile_sched(smle_csr_t a, Partition *p, int grid, const int **sched, const int **off)
+{
+    *sched = *off = nullptr;
+    static int enabled = -1;
+    if (enabled < 0) enabled = env_int("SMLE_SPMM_SCHED", 1);
+    if (!enabled) return SMLE_OK;
+    auto found = p->scheds.find(grid);
+    if (found != p->scheds.end()) { *sched = found->second.sched; *off = found->second.off; return SMLE_OK; }
+    Partition::Sched sc;
+    int D = 0;
+    int rc = far_stride(a, &D);
+    if (rc) return rc;
+    const int T = p->num_tiles;
+    const double rows_per_tile = (double)a->m / (double)(T > 0 ? T : 1);
+    if (D > 0 && (double)D >= 8.0 * rows_per_tile && T >= 4 * grid) {
+        std::vector<int2> xy((size_t)T + 1);
+        CU(cudaMemcpyAsync(xy.data(), p->xy, sizeof(int2) * xy.size(), cudaMemcpyDeviceToHost, g_stream));
+        CU(cudaStreamSynchronize(g_stream));
+        std::vector<int> first((size_t)T);
+        for (int t = 0; t < T; ++t) first[(size_t)t] = xy[(size_t)t].x;
+        // successor of tile t: the tile that owns row first[t] + D
+        std::vector<char> used((size_t)T, 0);
+        std::vector<std::vector<int>> chains;
+        for (int t = 0; t < T; ++t) {
+            if (used[(size_t)t]) continue;
+            chains.emplace_back();
+            int c = t;
+            while (c < T && !used[(size_t)c]) {
+                used[(size_t)c] = 1;
+                chains.back().push_back(c);
+                const long long want = (long long)first[(size_t)c] + D;
+                if (want >= a->m) break;
+                c = (int)(std::upper_bound(first.begin(), first.end(), (int)want) - first.begin()) - 1;
+            }
+        }
+        // segment length: the deal must balance (units per CTA x tiles per unit close to T / grid)
+        size_t longest = 0;
+        for (auto &ch : chains) longest = std::max(longest, ch.size());
+        // cost of a segment length = tiles on the busiest CTA + 0.3 tile-times per segment start (its first
+        // tile finds none of its -D rows in L1)
+        double best_cost = -1.0;
+        int best_seg = 0;
+        for (int seg = (int)longest; seg >= 4; --seg) {
+            long long units = 0;
+            for (auto &ch : chains) units += ((long long)ch.size() + seg - 1) / seg;
+            const long long per_cta = (units + grid - 1) / grid;
+            const double cost = (double)(per_cta * seg) + 0.3 * (double)per_cta;
+            if (best_cost < 0 || cost < best_cost) { best_cost = cost; best_seg = seg; }
+        }
+        if (best_seg > 0) {
+            struct Unit { int first, chain, begin, len; };
+            std::vector<Unit> units;
+            for (int ci2 = 0; ci2 < (int)chains.size(); ++ci2)
+                for (int b0 = 0; b0 < (int)chains[(size_t)ci2].size(); b0 += best_seg)
+                    units.push_back({chains[(size_t)ci2][(size_t)b0], ci2, b0, std::min(best_seg, (int)chains[(size_t)ci2].size() - b0)});
+            std::sort(units.begin(), units.end(), [](const Unit &x, const Unit &y) { return x.first < y.first; });
+            std::vector<int> h_off((size_t)grid + 1, 0), h_sched;
+            h_sched.reserve((size_t)T + grid);
+            for (int b = 0; b < grid; ++b) {
+                for (size_t u = (size_t)b; u < units.size(); u += (size_t)grid)
+                    for (int i = 0; i < units[u].len; ++i) h_sched.push_back(chains[(size_t)units[u].chain][(size_t)(units[u].begin + i)]);
+                h_sched.push_back(T);   // sentinel: end of this CTA's list
+                h_off[(size_t)b + 1] = (int)h_sched.size();
+            }
+            if ((int)h_sched.size() == T + grid) {
+                CU(cudaMalloc(&sc.sched, sizeof(int) * h_sched.size()));
+                CU(cudaMalloc(&sc.off, sizeof(int) * ((size_t)grid + 1)));
+                CU(cudaMemcpyAsync(sc.sched, h_sched.data(), sizeof(int) * h_sched.size(), cudaMemcpyHostToDevice, g_stream));
+                CU(cudaMemcpyAsync(sc.off, h_off.data(), sizeof(int) * ((size_t)grid + 1), cudaMemcpyHostToDevice, g_stream));
+                CU(cudaStreamSynchronize(g_stream));
+            }
+        }
+    }
+    p->scheds[grid] = sc;
+    *sched = sc.sched; *off = sc.off;
+    return SMLE_OK;
+}
+
 template <typename V, int G, int VEC, int NV, int UB, int THREADS, int TILE, int STAGES, int MINB, bool DOT>
 int launch_spmm_rows_t(smle_csr_t a, const V *X, V *Y, int k, const CgScalars &cg, bool dry)
 {
@@ -367,10 +488,13 @@ int launch_spmm_rows_t(smle_csr_t a, const V *X, V *Y, int k, const CgScalars &c
         if (occ < 1) return fail(SMLE_ERR_CUDA, "spmm_rows_kernel does not fit on an SM (%zu B smem)", smem);
         if (occ > MINB) occ = MINB;
     }
-    if (dry) return SMLE_OK;
     int grid = g_sms * occ;
     if (grid > a->max_ctas) grid = a->max_ctas;
     if (grid > p->num_tiles) grid = p->num_tiles;
+    const int *sched = nullptr, *sched_off = nullptr;
+    rc = get_tile_sched(a, p, grid, &sched, &sched_off);   // built once per (partition, grid): part of the lazy setup
+    if (rc) return rc;
+    if (dry) return SMLE_OK;
     // consecutive tiles per deal: 1 everywhere except the 16-lane shape (k = 32 fp64 / 64 fp32), where 2
     // measured 5 % faster (profiles/r01_spmm_sweeps.txt); SMLE_SPMM_CHUNK overrides, 0 = contiguous runs
     static int chunk_env = -2;
@@ -381,6 +505,7 @@ int launch_spmm_rows_t(smle_csr_t a, const V *X, V *Y, int k, const CgScalars &c
     args.X = X; args.Y = Y; args.tile_xy = p->xy;
     args.m = a->m; args.nnz = a->nnz; args.k = k;
     args.num_tiles = p->num_tiles; args.chunk = chunk;
+    args.sched = sched; args.sched_off = sched_off;
     args.tile_carry = (V *)a->tile_carry;
     args.dot_part = (V *)a->dot_part;
     args.ticket = a->ticket;
@@ -541,6 +666,7 @@ int launch_spmv(smle_csr_t a, const V *x, V *y, const CgScalars &cg, bool dry)
     switch (spmv_cfg()) {
 #define SMLE_CFG(th, i, st) case th * 10000 + i * 100 + st: return launch_spmv_t<V, th, i, st, DOT>(a, x, y, cg, dry);
         SMLE_CFG(480, 6, 2) SMLE_CFG(480, 5, 2) SMLE_CFG(480, 7, 2) SMLE_CFG(256, 12, 2) SMLE_CFG(224, 8, 2) SMLE_CFG(960, 4, 2)
+        SMLE_CFG(480, 4, 3) SMLE_CFG(480, 3, 4) SMLE_CFG(320, 6, 3) SMLE_CFG(640, 6, 2)
 #undef SMLE_CFG
     }
     return fail(SMLE_ERR_ARG, "unsupported SMLE_SPMV_CFG");
@@ -1050,7 +1176,10 @@ void smle_csr_destroy(smle_csr_t a)
     if (!a) return;
     if (g_stream) cudaStreamSynchronize(g_stream);
     free_workspace(a->ws);
-    for (auto &kv : a->parts) { cudaFree(kv.second.xy); cudaFree(kv.second.maxlen); cudaFree(kv.second.halo); }
+    for (auto &kv : a->parts) {
+        cudaFree(kv.second.xy); cudaFree(kv.second.maxlen); cudaFree(kv.second.halo);
+        for (auto &sc : kv.second.scheds) { cudaFree(sc.second.sched); cudaFree(sc.second.off); }
+    }
     cudaFree(a->ro); cudaFree(a->ci); cudaFree(a->va);
     cudaFree(a->carry_row); cudaFree(a->carry_val); cudaFree(a->dot_part); cudaFree(a->fix_part);
     cudaFree(a->ticket); cudaFree(a->tile_carry); cudaFree(a->cta_slot);

@@ -14,6 +14,13 @@
 //     moment the whole GPU works on one compact window of rows.  The dense block does not fit in
 //     L2 (2 GB at 200^3 x 32), but the window plus the off-diagonal planes it touches does, so
 //     every dense row comes from DRAM once instead of once per stencil plane;
+//   * when the matrix has a dominant far stride D (the w^2 plane offset of a 3-D stencil; detected
+//     from a sample of rows when the handle first runs an SpMM), the deal becomes a SCHEDULE: a CTA
+//     walks a chain of tiles D rows apart, so the dense rows it fetched as the +D neighbours of one
+//     tile are the rows it owns in the next and the -D neighbours of the one after -- L1 hits
+//     instead of two more trips to L2 per row.  Chains are cut into segments and dealt so that
+//     the CTAs working at the same time still share one compact window of rows (DRAM traffic stays
+//     compulsory) and finish together;
 //   * a WORKER of G lanes owns one row at a time and covers G*VEC = min(k, 32*VEC) columns with
 //     VEC-wide (128-bit) loads of the dense rows: every nonzero (broadcast from shared memory) is
 //     reused across all k right-hand sides.  The loads of a pass are unconditional (what lies
@@ -33,6 +40,21 @@
 #include "smle_spmv.cuh"
 
 namespace smle {
+
+// Structure probe for the tile schedule: column offsets (col - row) of the first kSampleNnz nonzeros
+// of `nsamples` evenly spaced rows (INT_MIN where the row is shorter).  Host code looks for a far
+// offset that most rows share (smle_capi.cu, far_stride()).
+constexpr int kSampleNnz = 16;
+
+__global__ void sample_offsets_kernel(const int *__restrict__ ro, const int *__restrict__ ci, int m, int nsamples,
+                                      int *__restrict__ out)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nsamples) return;
+    const int row = (int)((long long)i * m / nsamples);
+    const int beg = ro[row], end = ro[row + 1];
+    for (int j = 0; j < kSampleNnz; ++j) out[i * kSampleNnz + j] = (beg + j < end) ? ci[beg + j] - row : INT_MIN;
+}
 
 // L2-coherent (volatile) vector access to a carry slot: VEC*sizeof(V) in {4, 8, 16} bytes
 template <typename V, int VEC>
@@ -101,8 +123,10 @@ struct SpmmSmem {
     static constexpr int COL_WORDS = TILE + 24;
     static constexpr int VAL_ELEMS = TILE + 2 * EPV;
     static constexpr int RO_WORDS = TILE + 8;
-    static constexpr size_t STAGE_BYTES =
+    static constexpr size_t HDR_OFFSET =
         ((size_t)COL_WORDS * 4 + (size_t)VAL_ELEMS * sizeof(V) + (size_t)RO_WORDS * 4 + 15) / 16 * 16;
+    // tile header written by the producer: {tile id (-1: no more tiles), lo.x, lo.y, hi.x, hi.y}
+    static constexpr size_t STAGE_BYTES = HDR_OFFSET + 32;
 };
 
 constexpr int kSpmmRot = 17;   // worker rotation per tile
@@ -118,6 +142,8 @@ struct SpmmArgs {
     int m, nnz, k;
     int num_tiles;
     int chunk;                         // consecutive tiles a CTA takes before the deal moves on
+    const int *sched;                  // structure-aware tile schedule: the tiles of CTA b in processing order start at
+    const int *sched_off;              //   sched[sched_off[b]] and end with the sentinel num_tiles; NULL -> the deal above
     V *tile_carry;                     // [num_tiles * k] carry slots, sentinel when empty
     V *dot_part;                       // [gridDim.x * k]  (DOT)
     unsigned int *ticket;
@@ -198,7 +224,12 @@ spmm_rows_kernel(SpmmArgs<V> a, CgScalars cg)
     // tile schedule: iteration `it` of CTA b -> tile ((it / chunk) * grid + b) * chunk + it % chunk
     const int chunk = a.chunk;
     const int stride = (int)gridDim.x * chunk;
-    auto tile_of = [&](int it) { return (it / chunk) * stride + (int)blockIdx.x * chunk + it % chunk; };
+    // (every CTA's list ends with the sentinel num_tiles, so no count has to stay live in a register)
+    const int my_base = a.sched ? a.sched_off[blockIdx.x] : 0;
+    auto tile_of = [&](int it) {
+        if (a.sched) return __ldg(a.sched + my_base + it);
+        return (it / chunk) * stride + (int)blockIdx.x * chunk + it % chunk;
+    };
 
     auto stage_col = [&](int s) { return reinterpret_cast<int *>(smem_raw + (size_t)s * SM::STAGE_BYTES); };
     auto stage_val = [&](int s) {
@@ -208,6 +239,7 @@ spmm_rows_kernel(SpmmArgs<V> a, CgScalars cg)
         return reinterpret_cast<int *>(smem_raw + (size_t)s * SM::STAGE_BYTES + (size_t)SM::COL_WORDS * 4 +
                                        (size_t)SM::VAL_ELEMS * sizeof(V));
     };
+    auto stage_hdr = [&](int s) { return reinterpret_cast<int *>(smem_raw + (size_t)s * SM::STAGE_BYTES + SM::HDR_OFFSET); };
 
     if (tid == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(&s_full[s], 1); mbar_init(&s_empty[s], NW); }
@@ -233,13 +265,22 @@ spmm_rows_kernel(SpmmArgs<V> a, CgScalars cg)
             const uint64_t pol_stream = l2_policy_evict_first();
             for (int it = 0;; ++it) {
                 const int t = tile_of(it);
-                if (t >= a.num_tiles) break;
                 const int s = it % STAGES;
-                const int2 lo = a.tile_xy[t], hi = a.tile_xy[t + 1];
                 if (it >= STAGES) {
                     mbar_wait(&s_empty[s], (uint32_t)(it / STAGES - 1) & 1u);
                     fence_proxy_async();
                 }
+                // The tile's identity travels with its data: the consumers read the header after the wait
+                // on "full" (the arrive below releases these stores) and never touch the schedule or the
+                // coordinate array themselves -- no global loads, no registers held across the tile.
+                int *hdr = stage_hdr(s);
+                if (t >= a.num_tiles) {
+                    hdr[0] = -1;
+                    mbar_arrive(&s_full[s]);
+                    break;
+                }
+                const int2 lo = a.tile_xy[t], hi = a.tile_xy[t + 1];
+                hdr[0] = t; hdr[1] = lo.x; hdr[2] = lo.y; hdr[3] = hi.x; hdr[4] = hi.y;
                 const int yc = lo.y & ~3, yv = lo.y & ~(EPV - 1), rb = (lo.x + 1) & ~3;
                 const uint32_t nb_col = (uint32_t)((hi.y - yc + 3) & ~3) * 4u;
                 const uint32_t nb_val = (uint32_t)((hi.y - yv + EPV - 1) & ~(EPV - 1)) * (uint32_t)sizeof(V);
@@ -256,21 +297,14 @@ spmm_rows_kernel(SpmmArgs<V> a, CgScalars cg)
         const uint64_t pol_y = l2_policy_evict_first();
         const int num_cb = DOT ? 1 : (a.k + KB - 1) / KB;
         const unsigned kbytes = (unsigned)a.k * (unsigned)sizeof(V);   // bytes per dense row
-        int2 nxt_lo = make_int2(0, 0), nxt_hi = make_int2(0, 0);
-        {
-            const int t = tile_of(0);
-            if (t < a.num_tiles) { nxt_lo = a.tile_xy[t]; nxt_hi = a.tile_xy[t + 1]; }
-        }
         for (int it = 0;; ++it) {
-            const int t = tile_of(it);
-            if (t >= a.num_tiles) break;
             const int s = it % STAGES;
             const uint32_t parity = (uint32_t)(it / STAGES) & 1u;
-            const int2 lo = nxt_lo, hi = nxt_hi;
-            {
-                const int tn = tile_of(it + 1);
-                if (tn < a.num_tiles) { nxt_lo = a.tile_xy[tn]; nxt_hi = a.tile_xy[tn + 1]; }
-            }
+            mbar_wait(&s_full[s], parity);
+            const int *hdr = stage_hdr(s);
+            const int t = hdr[0];
+            if (t < 0) break;
+            const int2 lo = make_int2(hdr[1], hdr[2]), hi = make_int2(hdr[3], hdr[4]);
             const int x0 = lo.x, y0 = lo.y;
             const int rows = hi.x - x0, nz = hi.y - y0;
             const int yc = y0 & ~3, yv = y0 & ~(EPV - 1), rb = (x0 + 1) & ~3;
@@ -284,8 +318,6 @@ spmm_rows_kernel(SpmmArgs<V> a, CgScalars cg)
             // rotate the worker -> row map from tile to tile: with rows % W != 0 the same workers would
             // otherwise take the extra row of every tile
             const int wrot = (w + it * kSpmmRot) % W;
-
-            mbar_wait(&s_full[s], parity);
 
             for (int cb = 0; cb < num_cb; ++cb) {
                 // columns of this lane; lanes past k read column block 0 instead and store nothing

@@ -5,22 +5,23 @@
 // but laid out for one right-hand side, where the kernel is a pure HBM stream of the CSR arrays
 // (12 B per nonzero in fp64) plus an L1/L2-resident gather of x:
 //
-//   * persistent CTAs, each owning a contiguous run of tiles of TILE = 256*IPT merge items;
+//   * persistent CTAs, each owning a contiguous run of tiles of TILE = THREADS*IPT merge items;
 //   * the tile's column indices, values and row offsets are brought into shared memory by the
 //     TMA engine (cp.async.bulk, 1-D, completion on an mbarrier) STAGES tiles ahead of the
 //     compute, with an L2 evict-first policy -- the matrix is streamed once per SpMV and must
 //     not push the CG vectors out of the 126 MB L2;
-//   * phase A (coalesced, branch-free): every staged nonzero becomes value * x[column], written
-//     back in place; 128-bit shared-memory accesses, all gathers of a thread issued back to back;
-//   * phase B: each thread finds its diagonal with the reference's binary search (in shared
-//     memory) and reduces exactly IPT merge items; completed rows go to a shared row buffer,
-//     the first row of every thread waits for its carry-in;
-//   * carries: warp-shuffle segmented scan keyed by row -> per-tile -> per-CTA; the row cut by a
-//     CTA boundary is finished wait-free through one global slot per boundary (the party that
-//     arrives second adds owner part + carry, merge_based.hpp:137-149 semantics), so a plain SpMV
-//     has no last-CTA epilogue at all;
-//   * phase C: the tile's rows are written to y with coalesced stores; with DOT the products
-//     y[r]*x[r] (the p.Ap of CG) are accumulated from the same registers.
+//   * regular tiles (no row segment longer than 32, every stencil): one thread per row straight from
+//     the stage buffers -- adjacent lanes own adjacent rows, so a warp's gathers of x fall into 2-3
+//     cache lines and y is written coalesced; no CTA-wide barrier, warps drift across tiles;
+//   * general tiles (R-MAT hubs, the wheel's spoke row): the same pass, plus a warp-private reduction
+//     for rows of 33..1024 nonzeros (lanes stride over the row, shuffle tree) and a CTA-wide strided
+//     reduction for the rare longer segment (at most two per tile) -- the only barriers on the
+//     data path; the classic per-thread merge walk with its three barriers per tile is gone;
+//   * carries: per-tile -> per-CTA in shared memory; the row cut by a CTA boundary is finished
+//     wait-free through one global slot per boundary (the party that arrives second adds owner
+//     part + carry, merge_based.hpp:137-149 semantics), so a plain SpMV has no last-CTA epilogue;
+//   * with DOT the products y[r]*x[r] (the p.Ap of CG) are accumulated from the same registers; the
+//     dot product is linear in the parts of a row, so carries add their share where they are formed.
 #pragma once
 #include <type_traits>
 
@@ -119,14 +120,16 @@ struct SpmvSmem {
     static constexpr int COL_WORDS = TILE + 8;                       // staged column indices
     static constexpr int VAL_ELEMS = TILE + 2 * EPV;                 // staged values
     static constexpr int RO_WORDS = TILE + 8;                        // staged row offsets
-    static constexpr size_t STAGE_BYTES =
+    static constexpr size_t HDR_OFFSET =
         ((size_t)COL_WORDS * 4 + (size_t)VAL_ELEMS * sizeof(V) + (size_t)RO_WORDS * 4 + 15) / 16 * 16;
-    // the row buffer of phase B/C aliases the column-index region (free after phase A)
-    static constexpr int YBUF_ROWS = (COL_WORDS * 4) / (int)sizeof(V);
+    // tile header written by the producer: {lo.x, lo.y, hi.x, hi.y, longest row segment, gathers halo columns}
+    static constexpr size_t STAGE_BYTES = HDR_OFFSET + 32;
 };
 
 // longest in-tile row segment for which the fused thread-per-row path is used
 constexpr int kRowPathMaxLen = 32;
+// longest row segment one warp reduces by itself; longer ones are strided over by the whole CTA
+constexpr int kWarpRowMax = 1024;
 
 // One warp per tile: the longest run of nonzeros of a single row inside the tile (complete rows,
 // the leading part of row x0 and the trailing part of row x1).  A property of the matrix and the
@@ -226,6 +229,25 @@ __device__ __forceinline__ V row_sum(const V *__restrict__ x, const int *pc, con
     return sum;
 }
 
+// Partial sum of one row segment [beg, end) over the positions beg + id, beg + id + STRIDE, ...
+// (id < STRIDE): the lanes of a warp (STRIDE = 32) or the threads of the CTA stride over a long row.
+// Four gathers are requested before the first FMA; slots past the end repeat the last nonzero.
+template <typename V, bool COH, int STRIDE>
+__device__ __forceinline__ V strided_sum(const V *__restrict__ x, const int *pc, const V *pv, int beg, int end, int id)
+{
+    constexpr int UB = 4;
+    V sum = 0;
+    for (int z = beg + id; z < end; z += STRIDE * UB) {
+        V xa[UB];
+#pragma unroll
+        for (int j = 0; j < UB; ++j) xa[j] = gather<V, COH>(x + pc[min(z + j * STRIDE, end - 1)]);
+#pragma unroll
+        for (int j = 0; j < UB; ++j)
+            if (z + j * STRIDE < end) sum += pv[z + j * STRIDE] * xa[j];
+    }
+    return sum;
+}
+
 // Publisher side of the CTA-boundary exchange.  val = sum of the parts of row R = (row in progress
 // at the end of CTA c) that lie in CTAs <= c.  If the owner's part is already in slot c, finish the
 // row (owner part + carry); if CTA c+1 lies entirely inside the row, add its part and move on.
@@ -260,9 +282,8 @@ __device__ __noinline__ void cta_carry_publish(const int2 *__restrict__ tile_xy,
 //   consumers, regular tile (longest in-tile row segment <= kRowPathMaxLen, the common case):
 //       wait "full" -> thread-per-row gather + FMA straight from the stage buffers -> arrive
 //       on "empty".  NO CTA-wide barrier: warps drift freely across tiles.
-//   consumers, general tile (long or wildly uneven rows): phase A products in place ->
-//       consumer barrier -> merge-path walk of IPT items per thread -> warp-shuffle segmented
-//       scan of the carries -> coalesced row output.
+//   consumers, general tile (long or wildly uneven rows): the same pass; rows of 33..1024 nonzeros
+//       are reduced by the warp that found them, longer segments by the whole CTA.
 //   carries: every tile records (first row, has-complete-row, carry-out) in shared memory;
 //       thread 0 chains them in tile order every kChainTiles tiles and the fix-ups are applied
 //       in parallel (reference semantics: merge_based.hpp:137-149, carry added after the row's
@@ -280,8 +301,8 @@ spmv_kernel(SpmvArgs<V> a, CgScalars cg)
 
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ uint64_t s_full[STAGES], s_empty[STAGES];
-    __shared__ int s_wkey_first[NW], s_wkey_last[NW];
     __shared__ V s_wsum[NW];
+    __shared__ int s_huge[4], s_nhuge;       // row segments longer than kWarpRowMax in the current tile
     __shared__ V s_tcarry[kChainTiles];      // carry-out of each tile of the current chunk
     __shared__ int s_trow[kChainTiles];      // first row of the tile, or -1 when no row completes in it
     __shared__ V s_running;                  // carry chained so far (row in progress at the chunk start)
@@ -310,11 +331,13 @@ spmv_kernel(SpmvArgs<V> a, CgScalars cg)
         return reinterpret_cast<int *>(smem_raw + (size_t)s * SM::STAGE_BYTES + (size_t)SM::COL_WORDS * 4 +
                                        (size_t)SM::VAL_ELEMS * sizeof(V));
     };
+    auto stage_hdr = [&](int s) { return reinterpret_cast<int *>(smem_raw + (size_t)s * SM::STAGE_BYTES + SM::HDR_OFFSET); };
 
     if (tid == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(&s_full[s], 1); mbar_init(&s_empty[s], NW); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         s_running = 0;
+        s_nhuge = 0;
     }
     __syncthreads();
 
@@ -332,6 +355,12 @@ spmv_kernel(SpmvArgs<V> a, CgScalars cg)
                     mbar_wait(&s_empty[s], (uint32_t)(it / STAGES - 1) & 1u);
                     fence_proxy_async();
                 }
+                // the tile's coordinates and class travel with its data (released by the arrive below):
+                // the consumers read them from shared memory after the wait on "full"
+                int *hdr = stage_hdr(s);
+                hdr[0] = lo.x; hdr[1] = lo.y; hdr[2] = hi.x; hdr[3] = hi.y;
+                hdr[4] = a.tile_maxlen[t];
+                hdr[5] = a.tile_halo ? (int)a.tile_halo[t] : 0;
                 const int yc = lo.y & ~3;                                   // 16 B aligned column start
                 const int yv = lo.y & ~(EPV - 1);                           // 16 B aligned value start
                 const int rb = (lo.x + 1) & ~3;                             // 16 B aligned row-offset start
@@ -350,27 +379,17 @@ spmv_kernel(SpmvArgs<V> a, CgScalars cg)
         // The producer above streams the (immutable) matrix right away; x and y belong to the previous
         // kernel until it has completed.
         if constexpr (DOT) { griddep_wait(); griddep_launch_dependents(); }
-        // tile metadata is fetched one tile ahead so its latency hides behind the previous tile
-        int2 nxt_lo = make_int2(0, 0), nxt_hi = make_int2(0, 0);
-        int nxt_ml = 0;
-        bool nxt_halo = false, halo_ready = false;
-        if (t0 < t1) {
-            nxt_lo = a.tile_xy[t0]; nxt_hi = a.tile_xy[t0 + 1]; nxt_ml = a.tile_maxlen[t0];
-            if (a.tile_halo) nxt_halo = a.tile_halo[t0] != 0;
-        }
-
+        bool halo_ready = false;
         for (int t = t0; t < t1; ++t) {
             const int it = t - t0, s = it % STAGES, slot = it % kChainTiles;
             const uint32_t parity = (uint32_t)(it / STAGES) & 1u;
-            const int2 lo = nxt_lo, hi = nxt_hi;
-            const int tile_ml = nxt_ml;
-            const bool tile_halo = nxt_halo;
-            if (t + 1 < t1) {
-                nxt_lo = hi; nxt_hi = a.tile_xy[t + 2]; nxt_ml = a.tile_maxlen[t + 1];
-                if (a.tile_halo) nxt_halo = a.tile_halo[t + 1] != 0;
-            }
+            mbar_wait(&s_full[s], parity);
+            const int *hdr = stage_hdr(s);
+            const int2 lo = make_int2(hdr[0], hdr[1]), hi = make_int2(hdr[2], hdr[3]);
+            const int tile_ml = hdr[4];
+            const bool tile_halo = hdr[5] != 0;
             const int x0 = lo.x, y0 = lo.y;
-            const int rows = hi.x - x0, nz = hi.y - y0, items = rows + nz;
+            const int rows = hi.x - x0, nz = hi.y - y0;
             const int yc = y0 & ~3, yv = y0 & ~(EPV - 1), rb = (x0 + 1) & ~3;
             int *s_col = stage_col(s);
             V *s_val = stage_val(s);
@@ -380,7 +399,6 @@ spmv_kernel(SpmvArgs<V> a, CgScalars cg)
 
             if (tid == 0) s_trow[slot] = rows > 0 ? x0 : -1;
 
-            mbar_wait(&s_full[s], parity);
             // row-partitioned solve: only tiles that gather halo columns wait for the neighbours' push of
             // this iteration's p, and a warp waits ONCE per launch (the sys-scope acquire invalidates L1:
             // per tile it cost 100 us on the CTAs that own the boundary); interior tiles never look
@@ -397,7 +415,7 @@ spmv_kernel(SpmvArgs<V> a, CgScalars cg)
                     const int beg = (i == 0) ? 0 : s_re[i - 1] - y0;
                     const int end = (i == rows) ? nz : s_re[i] - y0;
                     const V sum = row_sum<V, decltype(coh)::value>(a.x, pc, pv, beg, end);
-                    V xr = 0;
+                    [[maybe_unused]] V xr = 0;
                     if constexpr (DOT) {
                         // after the gathers: x[row] was just fetched for the diagonal entry (an L1 hit) and the
                         // load does not take one of the few load slots while the gathers are in flight
@@ -413,128 +431,69 @@ spmv_kernel(SpmvArgs<V> a, CgScalars cg)
                 };
                 if (tile_halo) row_path(std::true_type{}); else row_path(std::false_type{});
             } else {
-                // ---- general tile, phase A: products in place -----------------------------------------
-                // Coalesced and branch-free: 16-byte groups of values and their columns are read with
-                // 128/64-bit shared loads, all gathers of the thread are issued before the first product
-                // is formed, and the products replace the values.  Groups at the tile edges may include
-                // nonzeros of the neighbouring tiles: their products are computed (the column is valid;
-                // the slack behind ci is zero-filled) and never read.
-                {
-                    const int nvec = (hi.y - yv + EPV - 1) / EPV;   // 16-byte groups staged
-                    constexpr int MAXIT = (SM::VAL_ELEMS / EPV + THREADS - 1) / THREADS;
-                    V xv[MAXIT][EPV];
-                    const int *cbase = s_col + (yv - yc);
+                // ---- general tile: rows of any length, three tiers, no merge walk -----------------------
+                //   <= kRowPathMaxLen  one thread per row segment (as above)
+                //   <= kWarpRowMax     the warp that found it reduces it: lanes stride over its nonzeros,
+                //                      shuffle tree; warp-private, no CTA barrier
+                //   longer             (a hub row: at most two such segments fit in a tile) the whole CTA
+                //                      strides over it; the only barriers of the kernel's data path
+                auto emit = [&](int i, V sum) {
+                    if (i < rows) {
+                        a.y[x0 + i] = sum;
+                        if constexpr (DOT) dot += sum * __ldg(a.x + x0 + i);
+                    } else {
+                        s_tcarry[slot] = sum;
+                    }
+                };
+                auto tiers = [&](auto coh) {
+                    constexpr bool COH = decltype(coh)::value;
+                    for (int base = 0; base <= rows; base += THREADS) {   // warp-uniform trip count (ballots inside)
+                        const int i = base + tid;
+                        const bool valid = i <= rows;
+                        int beg = 0, end = 0;
+                        if (valid) {
+                            beg = (i == 0) ? 0 : s_re[i - 1] - y0;
+                            end = (i == rows) ? nz : s_re[i] - y0;
+                        }
+                        const int len = end - beg;
+                        V sum = 0;
+                        if (valid && len <= kRowPathMaxLen) sum = row_sum<V, COH>(a.x, pc, pv, beg, end);
+                        unsigned med = __ballot_sync(0xffffffffu, valid && len > kRowPathMaxLen && len <= kWarpRowMax);
+                        while (med) {
+                            const int src = __ffs(med) - 1;
+                            med &= med - 1;
+                            const int b2 = __shfl_sync(0xffffffffu, beg, src), e2 = __shfl_sync(0xffffffffu, end, src);
+                            V part = strided_sum<V, COH, 32>(a.x, pc, pv, b2, e2, lane);
 #pragma unroll
-                    for (int q = 0; q < MAXIT; ++q) {
-                        const int g = tid + q * THREADS;           // group index
-                        if (g < nvec) {
-                            int c[EPV];
-                            if constexpr (EPV == 2) {
-                                int2 cc = *reinterpret_cast<const int2 *>(cbase + g * EPV);
-                                c[0] = cc.x; c[1] = cc.y;
-                            } else {
-                                int4 cc = *reinterpret_cast<const int4 *>(cbase + g * EPV);
-                                c[0] = cc.x; c[1] = cc.y; c[2] = cc.z; c[3] = cc.w;
+                            for (int d = 16; d > 0; d >>= 1) part += __shfl_xor_sync(0xffffffffu, part, d);
+                            if (lane == src) sum = part;
+                        }
+                        if (valid && len > kWarpRowMax) s_huge[atomicAdd(&s_nhuge, 1) & 3] = i;
+                        else if (valid) emit(i, sum);
+                    }
+                    if (tile_ml > kWarpRowMax) {   // uniform over the CTA: the tile's longest segment is known
+                        consumer_sync<THREADS>();
+                        const int nh = min(s_nhuge, 4);
+                        for (int h = 0; h < nh; ++h) {
+                            const int i = s_huge[h];
+                            const int beg = (i == 0) ? 0 : s_re[i - 1] - y0;
+                            const int end = (i == rows) ? nz : s_re[i] - y0;
+                            V part = strided_sum<V, COH, THREADS>(a.x, pc, pv, beg, end, tid);
+#pragma unroll
+                            for (int d = 16; d > 0; d >>= 1) part += __shfl_xor_sync(0xffffffffu, part, d);
+                            if (lane == 0) s_wsum[warp] = part;
+                            consumer_sync<THREADS>();
+                            if (tid == 0) {
+                                V total = 0;
+                                for (int wi = 0; wi < NW; ++wi) total += s_wsum[wi];
+                                emit(i, total);
+                                s_nhuge = 0;   // every thread has read it; the barrier below orders the reset
                             }
-#pragma unroll
-                            for (int e = 0; e < EPV; ++e) xv[q][e] = tile_halo ? gather<V, true>(a.x + c[e]) : gather<V, false>(a.x + c[e]);
+                            consumer_sync<THREADS>();
                         }
                     }
-#pragma unroll
-                    for (int q = 0; q < MAXIT; ++q) {
-                        const int g = tid + q * THREADS;
-                        if (g < nvec) {
-                            V v[EPV];
-                            ld_vec<V, EPV>(v, s_val + g * EPV);
-#pragma unroll
-                            for (int e = 0; e < EPV; ++e) v[e] *= xv[q][e];
-                            st_vec<V, EPV>(s_val + g * EPV, v);
-                        }
-                    }
-                }
-                consumer_sync<THREADS>();
-
-                // ---- general tile, phase B: merge-path walk, IPT items per thread -----------------------
-                V *s_y = reinterpret_cast<V *>(s_col);        // row buffer (columns are consumed)
-                const bool y_in_smem = rows <= SM::YBUF_ROWS;
-                const int d0 = min(tid * IPT, items);
-                int r_start;
-                {
-                    // MergePathSearch (merge_based.hpp:22-44) on the staged row-end offsets
-                    int l = max(d0 - nz, 0), h = min(d0, rows);
-                    while (l < h) {
-                        const int mid = (l + h) >> 1;
-                        if (s_re[mid] - y0 <= d0 - mid - 1) l = mid + 1; else h = mid;
-                    }
-                    r_start = l;
-                }
-                int r = r_start;
-                int z = d0 - r;
-                V acc = 0;
-                int cur_end = s_re[r] - y0;
-                const int n_items = min(IPT, items - d0);
-#pragma unroll
-                for (int i = 0; i < IPT; ++i) {
-                    const bool live = i < n_items;
-                    const bool is_nz = live && (z < cur_end);
-                    const V pz = pv[z];                       // always inside the stage buffer
-                    if (is_nz) { acc += pz; ++z; }
-                    if (live && !is_nz) {
-                        if (y_in_smem) s_y[r] = acc; else a.y[x0 + r] = acc;
-                        acc = 0;
-                        ++r;
-                        cur_end = s_re[r] - y0;
-                    }
-                }
-
-                // carries: inclusive segmented scan keyed by the row in progress
-                const int key = x0 + r;
-                V sc = acc;
-                {
-                    const int pkey = __shfl_up_sync(0xffffffffu, key, 1);
-                    const bool same = lane > 0 && pkey == key;
-                    if (__any_sync(0xffffffffu, same)) {   // a row spans several threads of this warp
-#pragma unroll
-                        for (int d = 1; d < 32; d <<= 1) {
-                            const int okey = __shfl_up_sync(0xffffffffu, key, d);
-                            const V o = __shfl_up_sync(0xffffffffu, sc, d);
-                            if (lane >= d && okey == key) sc += o;
-                        }
-                    }
-                }
-                if (lane == 31) { s_wkey_last[warp] = key; s_wsum[warp] = sc; }
-                if (lane == 0) s_wkey_first[warp] = key;
-                consumer_sync<THREADS>();
-                // full inclusive value of the previous warps' last threads (rows may chain across warps)
-                V wprev = 0;
-                for (int wi = 0; wi < warp; ++wi) {
-                    const bool chain = wi > 0 && s_wkey_first[wi] == s_wkey_last[wi] &&
-                                       s_wkey_last[wi - 1] == s_wkey_last[wi];
-                    wprev = s_wsum[wi] + (chain ? wprev : V(0));
-                }
-                const int wprev_key = warp > 0 ? s_wkey_last[warp - 1] : -1;
-                const int wfirst_key = s_wkey_first[warp];
-                const V sfull = sc + ((wfirst_key == key && wprev_key == key) ? wprev : V(0));
-                V carry_in = __shfl_up_sync(0xffffffffu, sfull, 1);
-                if (lane == 0) carry_in = wprev;
-                if (tid == 0) carry_in = 0;   // the tile's own carry-in is applied by the chain below
-                if (r > r_start) {            // this thread completed row r_start: it owns that entry
-                    if (y_in_smem) s_y[r_start] += carry_in;
-                    else a.y[x0 + r_start] += carry_in;
-                }
-                if (tid == THREADS - 1) s_tcarry[slot] = sfull;   // tile carry-out (row hi.x)
-                consumer_sync<THREADS>();
-
-                // phase C: coalesced row output (+ dot)
-                if (y_in_smem) {
-                    for (int i = tid; i < rows; i += THREADS) {
-                        const V v = s_y[i];
-                        a.y[x0 + i] = v;
-                        if constexpr (DOT) dot += v * __ldg(a.x + x0 + i);
-                    }
-                } else if constexpr (DOT) {
-                    for (int i = tid; i < rows; i += THREADS) dot += a.y[x0 + i] * __ldg(a.x + x0 + i);
-                }
+                };
+                if (tile_halo) tiers(std::true_type{}); else tiers(std::false_type{});
             }
 
             // release the stage: generic-proxy accesses ordered before the next bulk copy, one

@@ -1,6 +1,7 @@
 """Sweep SpMM kernel configurations in sub-processes and time SpMM / multi-RHS CG kernels.
 usage: python tools/sweep_spmm.py [grid_width] [k] cfg[@chunk] ...
-cfg = <threads>x<tile>x<stages>x<minb> (SMLE_SPMM_CFG), chunk = SMLE_SPMM_CHUNK, "v1" = merge-walk kernel"""
+cfg = <threads>x<tile>x<stages>x<minb> (SMLE_SPMM_CFG), chunk = SMLE_SPMM_CHUNK, "v1" = merge-walk kernel,
+"sched0" / "sched1" = default configuration without / with the structure-aware tile schedule"""
 import os
 import subprocess
 import sys
@@ -33,6 +34,8 @@ for spec in sys.argv[3:] or ["256x1024x2x2@2"]:
     env = dict(os.environ, SWEEP_TAG=spec)
     if spec == "v1":
         env["SMLE_SPMM_V1"] = "1"
+    elif spec in ("sched0", "sched1"):   # default configuration without / with the structure-aware tile schedule
+        env["SMLE_SPMM_SCHED"] = spec[-1]
     else:
         cfg, _, chunk = spec.partition("@")
         env["SMLE_SPMM_CFG"] = cfg
