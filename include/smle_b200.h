@@ -201,6 +201,9 @@ int smle_dist_cg_f64(smle_dist_t d, const double *b_local, double *x_local, int 
                      int is_device_ptr, int *iters_out, double *final_rel_res);
 /* per-kernel timing of the row-partitioned iteration, like smle_cg_profile_f64 (collective) */
 int smle_dist_cg_profile_f64(smle_dist_t d, const double *b_local_dev, int iters, float *ms_per_kernel);
+/* measurement aid: microseconds per all-reduce of one double through the peer-memory mailboxes
+ * (CUDA graph of post + wait kernel pairs; iters >= 64); collective */
+int smle_dist_allreduce_bench_f64(smle_dist_t d, int iters, double *us_each);
 void smle_dist_destroy(smle_dist_t d);
 
 /* ---- matrix / RHS generators (host side) -------------------------------------------------

@@ -1733,4 +1733,53 @@ int smle_dist_cg_profile_f64(smle_dist_t d, const double *b_local_dev, int iters
     return rc;
 }
 
+// A/B aid: `iters` back-to-back all-reduces of one double through the peer-memory mailboxes, replayed
+// from a CUDA graph of 64 (post + wait) pairs.  *us_each = microseconds per all-reduce on this rank.
+// Collective.
+int smle_dist_allreduce_bench_f64(smle_dist_t d, int iters, double *us_each)
+{
+    if (!d || iters < 64 || !us_each) return fail(SMLE_ERR_ARG, "bad argument (iters >= 64)");
+    if (!d->connected) return fail(SMLE_ERR_COMM, "smle_dist_connect has not been called");
+    int rc = ensure_workspace(d->a, 1, 0);
+    if (rc) return rc;
+    CgWorkspace &w = d->a->ws;
+    CgScalars cg = make_scalars(w, 1);
+    const int reps = iters / 64;
+    int ctrl[CTRL_WORDS] = {0, 0, 0, reps * 64 + 64 + 1, 0, d->seq_base, 0, 0};
+    CU(cudaMemcpyAsync(w.ctrl, ctrl, sizeof(ctrl), cudaMemcpyHostToDevice, g_stream));
+    const double one = 1.0;
+    CU(cudaMemcpyAsync(cg.rs_old, &one, sizeof(double), cudaMemcpyHostToDevice, g_stream));
+    cudaGraph_t graph;
+    cudaGraphExec_t exec;
+    CU(cudaStreamBeginCapture(g_stream, cudaStreamCaptureModeThreadLocal));
+    for (int i = 0; i < 64; ++i) {
+        dist_post_kernel<<<1, 32, 0, g_stream>>>(d->ctl, 0, cg.rs_old, cg.ctrl);
+        dist_allreduce_wait_kernel<<<1, 32, 0, g_stream>>>(d->ctl, cg.pAp, cg.ctrl);
+    }
+    cudaError_t e = cudaStreamEndCapture(g_stream, &graph);
+    if (e != cudaSuccess) return fail(SMLE_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(e));
+    e = cudaGraphInstantiate(&exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (e != cudaSuccess) return fail(SMLE_ERR_CUDA, "graph instantiate failed: %s", cudaGetErrorString(e));
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    cudaGraphLaunch(exec, g_stream);   // warm-up
+    cudaEventRecord(e0, g_stream);
+    for (int r = 0; r < reps; ++r) cudaGraphLaunch(exec, g_stream);
+    cudaEventRecord(e1, g_stream);
+    e = cudaStreamSynchronize(g_stream);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaGraphExecDestroy(exec);
+    g_launches += 2LL * 64 * (reps + 1);
+    d->seq_base += reps * 64 + 64 + 2;
+    if (e != cudaSuccess) return fail(SMLE_ERR_CUDA, "all-reduce bench failed: %s", cudaGetErrorString(e));
+    double sum = 0.0;
+    CU(cudaMemcpy(&sum, cg.pAp, sizeof(double), cudaMemcpyDeviceToHost));
+    if (sum != (double)d->world) return fail(SMLE_ERR_COMM, "all-reduce bench: sum %g != world %d", sum, d->world);
+    *us_each = 1e3 * ms / (reps * 64);
+    return SMLE_OK;
+}
+
 } // extern "C"

@@ -32,6 +32,16 @@ __global__ void dist_post_kernel(DistCtl d, int kind, const double *value, const
     dist_post(d, kind, *value, ctrl);
 }
 
+// Measurement aid (A/B against a library all-reduce): one all-reduce of a double through the mailboxes
+// = dist_post_kernel + this kernel, which waits for the G partials, writes their rank-ordered sum and
+// advances the iteration counter the sequence numbers derive from.
+__global__ void dist_allreduce_wait_kernel(DistCtl d, double *out, int *ctrl)
+{
+    const int it = ctrl[CTRL_ITER];
+    const double s = dist_wait_sum(d, 0, it & 1, dist_mail_seq(ctrl, 0, it));
+    if (threadIdx.x == 0) { *out = s; ctrl[CTRL_ITER] = it + 1; }
+}
+
 // K2 (distributed): alpha from the all-reduced p.Ap, r -= alpha*Ap, local r.r posted to every rank.
 // The first batch of r / Ap is requested BEFORE the mailbox wait, so the NVLink latency of the
 // reduction overlaps the DRAM latency of the sweep's first loads.

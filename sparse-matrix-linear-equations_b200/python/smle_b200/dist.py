@@ -256,3 +256,9 @@ class RowPartitionedCsr:
         out = (C.c_float * 3)()
         capi._check(capi.lib().smle_dist_cg_profile_f64(self._h, pb, _I(iters), out))
         return [float(v) for v in out]
+
+    def allreduce_bench(self, iters: int = 6400) -> float:
+        """microseconds per mailbox all-reduce of one double (measurement aid; collective)"""
+        us = _D(0)
+        capi._check(capi.lib().smle_dist_allreduce_bench_f64(self._h, _I(iters), C.byref(us)))
+        return us.value
