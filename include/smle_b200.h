@@ -137,6 +137,25 @@ int smle_cg_multi_f64(smle_csr_t a, const double *B, double *X, int k, int max_i
                       double *max_err_hist, int hist_capacity, int *hist_len,
                       double *final_rel_res);
 
+/* ---- SPAI-preconditioned multi-RHS CG -------------------------------
+ * smle_spai_build_f64 replaces SparseApproximateInversion
+ *   (work_2025/cg/sparse_approximate_inversion.hpp:41-321): HOST code, like the reference -- the
+ *   values of M on A's pattern (static pattern S_M = S_A, per-column least squares, symmetrised);
+ *   m_values[nnz] pairs with A's row_offsets / column_indices.
+ * smle_pcg_spai_multi_f64 replaces SPAISolveMultiple
+ *   (work_2025/main/sparse_approximate_inverse.hpp:31-230): `m` is a handle of M (same size as A);
+ *   per iteration two sparse products (A p with the fused p.Ap, z = M r with the fused r.z) and two
+ *   fused vector kernels; alpha is also 0 when p.Ap == 0 and beta when the old r.z == 0, the
+ *   convergence test sqrt(r.r)/||b|| < tol comes before the M step, as in the reference.
+ *   The reference's NONZERO_SPLIT kernel adds into the last row of its output instead of storing
+ *   it (nonzero_splitting.hpp:137-149), so SPAISolveMultiple, which does not clear Z / AP between
+ *   iterations, never converges with it; here all three `kernel` values compute Y = A X. */
+int smle_spai_build_f64(int m, int nnz, const int *row_offsets, const int *column_indices, const double *values,
+                        double *m_values);
+int smle_pcg_spai_multi_f64(smle_csr_t a, smle_csr_t m, const double *B, double *X, int k, int max_iters, double tol,
+                            int kernel, int is_device_ptr, int *iters_out, double *max_err_hist, int hist_capacity,
+                            int *hist_len, double *final_rel_res);
+
 /* Fixed-count variant for measurement: exactly `iters` CG iterations (no convergence exit),
  * device pointers only.  Same kernels and graph as smle_cg_multi_f64. */
 int smle_cg_run_fixed_f64(smle_csr_t a, const double *B, double *X, int k, int iters);

@@ -190,6 +190,39 @@ class _Backend:
                     _I(max_iters), ct(tol), _I(kernel), _ptr(hist), C.byref(hl))
         return int(it), X, hist[: hl.value].copy()
 
+    # -- SPAI (N3) -----------------------------------------------------------
+    def spai_build(self, ro, ci, va):
+        """values of the SPAI preconditioner M on A's pattern -- SparseApproximateInversion
+        (work_2025/cg/sparse_approximate_inversion.hpp:41-321)."""
+        m, nnz = len(ro) - 1, len(ci)
+        mv = np.zeros(nnz, dtype=np.float64)
+        fn = getattr(self._cg, f"{self._p}_spai_build_f64")
+        fn.restype = _I
+        dims = (_I(m), _I(m), _I(nnz)) if self._takes_n else (_I(m), _I(nnz))
+        rc = fn(*dims, _ptr(ro), _ptr(ci), _ptr(va), _ptr(mv))
+        if rc != 0:
+            raise RuntimeError("SPAI construction failed")
+        return mv
+
+    def spai_solve_multi(self, ro, ci, va, mv, B, k, max_iters, tol, kernel=MERGE, T=8):
+        """returns (iterations, X, max_error_history) -- SPAISolveMultiple
+        (work_2025/main/sparse_approximate_inverse.hpp:31-230)."""
+        m, nnz = len(ro) - 1, len(ci)
+        B = np.ascontiguousarray(B, dtype=np.float64)
+        X = np.empty((m, k), dtype=np.float64)
+        hist = np.zeros(max(max_iters, 1), dtype=np.float64)
+        hl = _I(0)
+        fn = getattr(self._cg, f"{self._p}_spai_solve_multi_f64")
+        fn.restype = _I
+        if self._p == "orc":
+            it = fn(_I(T), _I(m), _I(nnz), _ptr(ro), _ptr(ci), _ptr(va), _ptr(mv), _ptr(B), _ptr(X), _I(k),
+                    _I(max_iters), C.c_double(tol), _I(kernel), _ptr(hist), C.byref(hl))
+        else:
+            self.set_threads(T)
+            it = fn(_I(m), _I(m), _I(nnz), _ptr(ro), _ptr(ci), _ptr(va), _ptr(mv), _ptr(B), _ptr(X), _I(k),
+                    _I(max_iters), C.c_double(tol), _I(kernel), _ptr(hist), C.byref(hl))
+        return int(it), X, hist[: hl.value].copy()
+
     # -- generators ----------------------------------------------------------
     def _shape(self, name, *args):
         m, n, nnz = _I(0), _I(0), _I(0)

@@ -16,6 +16,7 @@
 #include "work_2025/hyper_parameters.hpp"
 #include "work_2025/main/no_pretreatment.hpp"
 #include "work_2025/main/single_strategy.hpp"
+#include "work_2025/main/sparse_approximate_inverse.hpp"
 
 namespace {
 
@@ -148,6 +149,30 @@ void ref_merge_path_search(int diagonal, const int *a, int a_len, int b_len, int
 
 REF_DEFINE(double, f64)
 REF_DEFINE(float, f32)
+
+// SPAI (rank "next" N3): SparseApproximateInversion (work_2025/cg/sparse_approximate_inversion.hpp:41-321,
+// static pattern S_M = S_A, per-column least squares through the shim's LAPACKE_dgels, symmetrised)
+// and SPAISolveMultiple (work_2025/main/sparse_approximate_inverse.hpp:31-230).
+int ref_spai_build_f64(int m, int n, int nnz, const int *ro, const int *ci, const double *va, double *m_values)
+{
+    CsrView<double> v(m, n, nnz, ro, ci, va);
+    CsrMatrix<double, int> l;
+    bool ok = SparseApproximateInversion(v.a, l);
+    if (ok) for (int i = 0; i < nnz; ++i) m_values[i] = l.values[i];
+    return ok ? 0 : 1;
+}
+
+int ref_spai_solve_multi_f64(int m, int n, int nnz, const int *ro, const int *ci, const double *va,
+                             const double *m_values, const double *B, double *X, int k, int max_iters, double tol,
+                             int kernel, double *hist, int *hist_len)
+{
+    CsrView<double> a(m, n, nnz, ro, ci, va), pm(m, n, nnz, ro, ci, m_values);
+    std::vector<double> errs;
+    int it = SPAISolveMultiple(a.a, pm.a, B, X, k, max_iters, tol, (SpmmKernel)kernel, hist ? &errs : nullptr);
+    if (hist) for (size_t i = 0; i < errs.size(); ++i) hist[i] = errs[i];
+    if (hist_len) *hist_len = (int)errs.size();
+    return it;
+}
 
 // CooMatrix::InitMarket (sparse_matrix.h:211-380) + CsrMatrix::Init; two-call protocol:
 // ro == NULL returns the shape only.

@@ -395,6 +395,201 @@ int FN(orc_cg_multi)(int T, int n, int nnz, const int *ro, const int *ci, const 
 }
 
 /* ------------------------------------------------------------------ */
+/* SPAI preconditioner                        */
+/* orc_spai_build restates SparseApproximateInversion                    */
+/*  (work_2025/cg/sparse_approximate_inversion.hpp:41-321): static       */
+/*  pattern S_M = S_A; for every column k, J = rows of A's column k,     */
+/*  I = union of the rows of A's columns j in J (in first-seen order),   */
+/*  minimise || A(I,J) m - e_k(I) ||_2 (:131-222; the reference calls    */
+/*  LAPACKE_?gels = Householder QR, restated in orc_lstsq), write m into */
+/*  M(J,k) through the CSC->CSR map (:226-238; zeros when the solve      */
+/*  fails :241-247), then symmetrise M = (M + M^T)/2 over the upper      */
+/*  triangle (:268-318).  Returns 0.                                     */
+/* ------------------------------------------------------------------ */
+static int FN(orc_lstsq)(int m, int n, VT *a, VT *b)
+{
+    /* row-major m x n (lda = n), m >= n; solution in b[0:n]; > 0: rank deficient */
+    if (m < n) return n + 1;
+    for (int j = 0; j < n; ++j) {
+        double nrm = 0.0;
+        for (int i = j; i < m; ++i) nrm += (double)a[i * n + j] * (double)a[i * n + j];
+        nrm = sqrt(nrm);
+        if (nrm == 0.0) return j + 1;
+        double ajj = (double)a[j * n + j], alpha = ajj > 0.0 ? -nrm : nrm, v0 = ajj - alpha;
+        double vv = v0 * v0;
+        for (int i = j + 1; i < m; ++i) vv += (double)a[i * n + j] * (double)a[i * n + j];
+        if (vv > 0.0) {
+            for (int c = j + 1; c <= n; ++c) {   /* c == n: the right-hand side */
+                double dot = v0 * (double)(c < n ? a[j * n + c] : b[j]);
+                for (int i = j + 1; i < m; ++i) dot += (double)a[i * n + j] * (double)(c < n ? a[i * n + c] : b[i]);
+                double f = 2.0 * dot / vv;
+                if (c < n) {
+                    a[j * n + c] = (VT)((double)a[j * n + c] - f * v0);
+                    for (int i = j + 1; i < m; ++i) a[i * n + c] = (VT)((double)a[i * n + c] - f * (double)a[i * n + j]);
+                } else {
+                    b[j] = (VT)((double)b[j] - f * v0);
+                    for (int i = j + 1; i < m; ++i) b[i] = (VT)((double)b[i] - f * (double)a[i * n + j]);
+                }
+            }
+        }
+        a[j * n + j] = (VT)alpha;
+    }
+    for (int j = n - 1; j >= 0; --j) {
+        double sacc = (double)b[j];
+        for (int c = j + 1; c < n; ++c) sacc -= (double)a[j * n + c] * (double)b[c];
+        b[j] = (VT)(sacc / (double)a[j * n + j]);
+    }
+    return 0;
+}
+
+int FN(orc_spai_build)(int m, int nnz, const int *ro, const int *ci, const VT *va, VT *mv)
+{
+    /* CSC of A with the map back to CSR positions (:88-118) */
+    int *co = (int *)calloc((size_t)m + 1, sizeof(int));
+    int *cr = (int *)malloc(sizeof(int) * (size_t)(nnz ? nnz : 1));
+    int *map = (int *)malloc(sizeof(int) * (size_t)(nnz ? nnz : 1));
+    VT *cv = (VT *)malloc(sizeof(VT) * (size_t)(nnz ? nnz : 1));
+    for (int z = 0; z < nnz; ++z) ++co[ci[z] + 1];
+    for (int c = 0; c < m; ++c) co[c + 1] += co[c];
+    {
+        int *pos = (int *)malloc(sizeof(int) * ((size_t)m + 1));
+        memcpy(pos, co, sizeof(int) * ((size_t)m + 1));
+        for (int r = 0; r < m; ++r)
+            for (int z = ro[r]; z < ro[r + 1]; ++z) {
+                int d = pos[ci[z]]++;
+                cr[d] = r; cv[d] = va[z]; map[d] = z;
+            }
+        free(pos);
+    }
+    for (int z = 0; z < nnz; ++z) mv[z] = 0;
+#pragma omp parallel
+    {
+        int *g2l = (int *)malloc(sizeof(int) * (size_t)(m ? m : 1));
+        for (int i = 0; i < m; ++i) g2l[i] = -1;
+        int cap_rows = 64, cap_dense = 1024;
+        int *rows = (int *)malloc(sizeof(int) * (size_t)cap_rows);
+        VT *dense = (VT *)malloc(sizeof(VT) * (size_t)cap_dense);
+        VT *rhs = (VT *)malloc(sizeof(VT) * (size_t)cap_rows);
+#pragma omp for schedule(static)
+        for (int k = 0; k < m; ++k) {
+            int j0 = co[k], nv = co[k + 1] - j0, ne = 0;
+            if (nv == 0) continue;
+            for (int q = j0; q < j0 + nv; ++q) {
+                int col = cr[q];
+                for (int t = co[col]; t < co[col + 1]; ++t) {
+                    int r = cr[t];
+                    if (g2l[r] == -1) {
+                        if (ne == cap_rows) {
+                            cap_rows *= 2;
+                            rows = (int *)realloc(rows, sizeof(int) * (size_t)cap_rows);
+                            rhs = (VT *)realloc(rhs, sizeof(VT) * (size_t)cap_rows);
+                        }
+                        g2l[r] = ne; rows[ne++] = r;
+                    }
+                }
+            }
+            if (ne * nv > cap_dense) { cap_dense = ne * nv; dense = (VT *)realloc(dense, sizeof(VT) * (size_t)cap_dense); }
+            for (int i = 0; i < ne * nv; ++i) dense[i] = 0;
+            for (int i = 0; i < ne; ++i) rhs[i] = 0;
+            if (g2l[k] != -1) rhs[g2l[k]] = 1;
+            for (int jl = 0; jl < nv; ++jl) {
+                int col = cr[j0 + jl];
+                for (int t = co[col]; t < co[col + 1]; ++t) dense[g2l[cr[t]] * nv + jl] = cv[t];
+            }
+            int info = FN(orc_lstsq)(ne, nv, dense, rhs);
+            for (int jl = 0; jl < nv; ++jl) mv[map[j0 + jl]] = info == 0 ? rhs[jl] : (VT)0;
+            for (int i = 0; i < ne; ++i) g2l[rows[i]] = -1;
+        }
+        free(g2l); free(rows); free(dense); free(rhs);
+    }
+    /* symmetrise over the upper triangle (:268-318) */
+#pragma omp parallel for schedule(static)
+    for (int r = 0; r < m; ++r)
+        for (int z = ro[r]; z < ro[r + 1]; ++z) {
+            int c = ci[z];
+            if (c <= r) continue;
+            for (int t = ro[c]; t < ro[c + 1]; ++t)
+                if (ci[t] == r) {
+                    VT avg = (mv[z] + mv[t]) * (VT)0.5;
+                    mv[z] = avg; mv[t] = avg;
+                    break;
+                }
+        }
+    free(co); free(cr); free(map); free(cv);
+    return 0;
+}
+
+/* ------------------------------------------------------------------ */
+/* SPAI-preconditioned multi-RHS CG -- restates SPAISolveMultiple        */
+/*  (work_2025/main/sparse_approximate_inverse.hpp:31-230): z = M r by   */
+/*  an SpMM with M, rs = r.z, alpha guarded against pAp == 0 (:121-127), */
+/*  beta against rs_old == 0 (:186-192), convergence on sqrt(r.r)/||b||  */
+/*  before the M step (:139-166).                                        */
+/* ------------------------------------------------------------------ */
+static void FN(orc_spmm_kernel)(int T, int kernel, int n, int nnz, const int *ro, const int *ci, const VT *va,
+                                const VT *X, VT *Y, int k)
+{
+    if (kernel == 0) FN(orc_row_split_csrmm)(T, n, ro, ci, va, X, Y, k);
+    else if (kernel == 1) FN(orc_merge_csrmm)(T, n, nnz, ro + 1, ci, va, X, Y, k);
+    else FN(orc_nonzero_split_csrmm)(T, n, nnz, ro + 1, ci, va, X, Y, k);
+}
+
+int FN(orc_spai_solve_multi)(int T, int n, int nnz, const int *ro, const int *ci, const VT *va, const VT *mv,
+                             const VT *B, VT *X, int k, int max_iters, VT tol, int kernel,
+                             double *hist, int *hist_len)
+{
+    size_t nk = (size_t)n * (size_t)k;
+    VT *R = (VT *)malloc(sizeof(VT) * nk), *P = (VT *)malloc(sizeof(VT) * nk);
+    VT *AP = (VT *)malloc(sizeof(VT) * nk), *Z = (VT *)malloc(sizeof(VT) * nk);
+    VT *alpha = (VT *)malloc(sizeof(VT) * (size_t)k), *beta = (VT *)malloc(sizeof(VT) * (size_t)k);
+    VT *rs_old = (VT *)malloc(sizeof(VT) * (size_t)k), *rs_new = (VT *)malloc(sizeof(VT) * (size_t)k);
+    VT *pAp = (VT *)malloc(sizeof(VT) * (size_t)k), *bn = (VT *)malloc(sizeof(VT) * (size_t)k);
+    char *done = (char *)calloc((size_t)k, 1);
+#pragma omp parallel for
+    for (long long i = 0; i < (long long)nk; ++i) { X[i] = 0.0; R[i] = B[i]; P[i] = 0.0; Z[i] = 0.0; }
+    FN(orc_dot_multi)(n, k, B, B, bn);
+    for (int i = 0; i < k; ++i) {
+        bn[i] = (VT)sqrt((double)bn[i]);
+        if (bn[i] == 0.0) bn[i] = 1.0;
+    }
+    FN(orc_spmm_kernel)(T, kernel, n, nnz, ro, ci, mv, R, Z, k);
+    memcpy(P, Z, sizeof(VT) * nk);
+    FN(orc_dot_multi)(n, k, R, Z, rs_old);
+    int nh = 0, it;
+    for (it = 0; it < max_iters; ++it) {
+        FN(orc_spmm_kernel)(T, kernel, n, nnz, ro, ci, va, P, AP, k);
+        FN(orc_dot_multi)(n, k, P, AP, pAp);
+        for (int i = 0; i < k; ++i) alpha[i] = (!done[i] && pAp[i] != 0.0) ? rs_old[i] / pAp[i] : (VT)0.0;
+        FN(orc_axpy_multi)(n, k, alpha, P, X);
+        for (int i = 0; i < k; ++i) alpha[i] = -alpha[i];
+        FN(orc_axpy_multi)(n, k, alpha, AP, R);
+        FN(orc_dot_multi)(n, k, R, R, pAp);
+        int ndone = 0;
+        double worst = 0.0;
+        for (int i = 0; i < k; ++i) {
+            double rel = sqrt((double)pAp[i]) / (double)bn[i];
+            if (rel > worst) worst = rel;
+            if (!done[i] && rel < (double)tol) done[i] = 1;
+            if (done[i]) ++ndone;
+        }
+        if (hist) hist[nh] = worst;
+        ++nh;
+        if (ndone == k) { ++it; break; }
+        FN(orc_spmm_kernel)(T, kernel, n, nnz, ro, ci, mv, R, Z, k);
+        FN(orc_dot_multi)(n, k, R, Z, rs_new);
+        for (int i = 0; i < k; ++i) {
+            beta[i] = (!done[i] && rs_old[i] != 0.0) ? rs_new[i] / rs_old[i] : (VT)0.0;
+            rs_old[i] = rs_new[i];
+        }
+        FN(orc_update_p_multi)(n, k, Z, beta, P);
+    }
+    if (hist_len) *hist_len = nh;
+    free(R); free(P); free(AP); free(Z); free(alpha); free(beta); free(rs_old); free(rs_new);
+    free(pAp); free(bn); free(done);
+    return it;
+}
+
+/* ------------------------------------------------------------------ */
 /* COO -> CSR, as CsrMatrix::Init (sparse_matrix.h:668-733):            */
 /* stable sort by (row, col), duplicates kept, then offsets fill.       */
 /* Input COO arrays are consumed (sorted in place via a scratch copy).  */

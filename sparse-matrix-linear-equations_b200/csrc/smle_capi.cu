@@ -132,6 +132,11 @@ struct CgWorkspace {
     cudaGraphExec_t graph = nullptr;                    // `graph_iters` iterations of K1,K2,K3
     int graph_iters = 0;
     unsigned graph_epoch = 0;                           // scratch_epoch of the handle when the graph was captured
+    // SPAI-preconditioned CG: z = M r, and the iteration graph (A step, x/r update, M step, p update)
+    double *Z = nullptr;
+    cudaGraphExec_t pcg_graph = nullptr;
+    const void *pcg_m = nullptr;                        // preconditioner handle the graph was captured with
+    unsigned pcg_epoch_a = 0, pcg_epoch_m = 0;
 };
 
 struct Partition {
@@ -173,6 +178,8 @@ namespace {
 void free_workspace(CgWorkspace &w)
 {
     if (w.graph) cudaGraphExecDestroy(w.graph);
+    if (w.pcg_graph) cudaGraphExecDestroy(w.pcg_graph);
+    cudaFree(w.Z);
     cudaFree(w.R); cudaFree(w.P); cudaFree(w.AP); cudaFree(w.Bd); cudaFree(w.Xd);
     cudaFree(w.Bd2[0]); cudaFree(w.Bd2[1]); cudaFree(w.Xs);
     cudaFree(w.scal); cudaFree(w.conv); cudaFree(w.ctrl); cudaFree(w.hist); cudaFree(w.part);
@@ -386,7 +393,7 @@ int get_tile_sched(smle_csr_t a, Partition *p, int grid, const int **sched, cons
 {
     *sched = *off = nullptr;
     static int enabled = -1;
-    if (enabled < 0) enabled = env_int("SMLE_SPMM_SCHED", 1);
+    if (enabled < 0) enabled = env_int("SMLE_SPMM_SCHED", 0);   // measured slower than the round-robin deal (profiles/r02_spmm_tile_schedule_ab.txt): off
     if (!enabled) return SMLE_OK;
     auto found = p->scheds.find(grid);
     if (found != p->scheds.end()) { *sched = found->second.sched; *off = found->second.off; return SMLE_OK; }
@@ -658,11 +665,21 @@ int spmv_cfg()   // threads*10000 + ipt*100 + stages
     return cfg;
 }
 
-int spmv_tile_items() { return (spmv_cfg() / 10000) * ((spmv_cfg() / 100) % 100); }
+bool spmv_cfg_forced() { return getenv("SMLE_SPMV_CFG") != nullptr; }
+
+int spmv_tile_items(smle_csr_t a)
+{
+    if (!spmv_cfg_forced() && (long long)a->m + a->nnz < 16LL * kSpmvThreads * kSpmvIPT * 2 * g_sms) return 480 * 4;
+    return (spmv_cfg() / 10000) * ((spmv_cfg() / 100) % 100);
+}
 
 template <typename V, bool DOT>
 int launch_spmv(smle_csr_t a, const V *x, V *y, const CgScalars &cg, bool dry)
 {
+    // small problems (fewer than ~16 default tiles per CTA, e.g. grid2d 1000^2: 7): tiles of 1920 items in 3
+    // stages start the first row sooner and drain faster (profiles/r02_spmv_grid2d_1000_cfg_sweep.jsonl)
+    if (!spmv_cfg_forced() && (long long)a->m + a->nnz < 16LL * kSpmvThreads * kSpmvIPT * 2 * g_sms)
+        return launch_spmv_t<V, 480, 4, 3, DOT>(a, x, y, cg, dry);
     switch (spmv_cfg()) {
 #define SMLE_CFG(th, i, st) case th * 10000 + i * 100 + st: return launch_spmv_t<V, th, i, st, DOT>(a, x, y, cg, dry);
         SMLE_CFG(480, 6, 2) SMLE_CFG(480, 5, 2) SMLE_CFG(480, 7, 2) SMLE_CFG(256, 12, 2) SMLE_CFG(224, 8, 2) SMLE_CFG(960, 4, 2)
@@ -787,6 +804,7 @@ int ensure_workspace(smle_csr_t a, int k, int hist_cap)
         CU(cudaMalloc(&w.hist, sizeof(double) * (size_t)hist_cap));
         w.hist_cap = hist_cap;
         if (w.graph) { cudaGraphExecDestroy(w.graph); w.graph = nullptr; }
+        if (w.pcg_graph) { cudaGraphExecDestroy(w.pcg_graph); w.pcg_graph = nullptr; }
     }
     return SMLE_OK;
 }
@@ -806,6 +824,7 @@ CgScalars make_scalars(CgWorkspace &w, int k)
     s.tol = w.scal + 6 * (size_t)k + 1;
     s.hist = w.hist;
     s.hist_cap = w.hist_cap;
+    s.dot_mode = DOT_CG_ALPHA;
     return s;
 }
 
@@ -1002,6 +1021,127 @@ int cg_solve(smle_csr_t a, const double *B, double *X, int k, int max_iters, dou
     if (!w.Bd) CU(cudaMalloc(&w.Bd, sizeof(double) * (w.nk ? w.nk : 1)));
     CU(cudaMemcpyAsync(w.Bd, B, sizeof(double) * w.nk, cudaMemcpyHostToDevice, g_stream));
     return cg_solve_device(a, w.Bd, nullptr, X, k, max_iters, tol, iters_out, hist, hist_capacity, hist_len, final_rel);
+}
+
+// ---- SPAI-preconditioned multi-RHS CG ---------------------------------------------------------------
+template <int G, int VEC>
+int launch_pcg_vec_t(int which, const CgVecArgs &va, const CgScalars &cg, int grid)
+{
+    if (which == 0) pcg_update_xr_kernel<G, VEC><<<grid, kThreads, 0, g_stream>>>(va, cg);
+    else pcg_update_p_kernel<G, VEC><<<grid, kThreads, 0, g_stream>>>(va, cg);
+    ++g_launches;
+    return check_launch("pcg vector kernel");
+}
+
+int launch_pcg_vec(int which, const CgVecArgs &va, const CgScalars &cg)
+{
+    int G, VEC;
+    pick_shape<double>(va.k, &G, &VEC);
+    const int W = kThreads / G;
+    long long want = ((long long)va.n + W - 1) / W;
+    int grid = (int)(want < (long long)g_sms * 8 ? want : (long long)g_sms * 8);
+    if (grid < 1) grid = 1;
+#define SMLE_CASE(g, v) if (G == g && VEC == v) return launch_pcg_vec_t<g, v>(which, va, cg, grid);
+    SMLE_CASE(1, 1) SMLE_CASE(2, 1) SMLE_CASE(4, 1) SMLE_CASE(8, 1) SMLE_CASE(16, 1) SMLE_CASE(32, 1)
+    SMLE_CASE(1, 2) SMLE_CASE(2, 2) SMLE_CASE(4, 2) SMLE_CASE(8, 2) SMLE_CASE(16, 2) SMLE_CASE(32, 2)
+#undef SMLE_CASE
+    return fail(SMLE_ERR_ARG, "no vector kernel for k=%d", va.k);
+}
+
+// z = M r with the fused r.z turned into rs_old / beta (mode), then p = z + beta p
+int pcg_m_step(smle_csr_t m, const CgVecArgs &va, CgScalars cg, int mode, bool dry = false)
+{
+    cg.dot_mode = mode;
+    int rc = launch_merge<double, true>(m, va.R, va.Z, va.k, cg, dry);
+    if (!rc && !dry) rc = launch_pcg_vec(1, va, cg);
+    return rc;
+}
+
+int pcg_iteration(smle_csr_t a, smle_csr_t m, const CgVecArgs &va, CgScalars cg)
+{
+    cg.dot_mode = DOT_PCG_ALPHA;
+    int rc = launch_merge<double, true>(a, va.P, va.AP, va.k, cg);
+    if (!rc) rc = launch_pcg_vec(0, va, cg);
+    if (!rc) rc = pcg_m_step(m, va, cg, DOT_PCG_BETA);
+    return rc;
+}
+
+int pcg_solve_device(smle_csr_t a, smle_csr_t m, const double *B, double *X_dev, double *X_host, int k, int max_iters,
+                     double tol, int *iters_out, double *hist_out, int hist_capacity, int *hist_len, double *final_rel)
+{
+    const bool want_hist = hist_out != nullptr && hist_capacity > 0;
+    int rc = ensure_workspace(a, k, want_hist ? (max_iters < hist_capacity ? max_iters : hist_capacity) : 0);
+    if (!rc) rc = ensure_scratch(a, k);
+    if (!rc) rc = ensure_scratch(m, k);
+    if (rc) return rc;
+    CgWorkspace &w = a->ws;
+    if (!w.Z) CU(cudaMalloc(&w.Z, sizeof(double) * (w.nk ? w.nk : 1)));
+    CgScalars cg = make_scalars(w, k);
+    CgVecArgs va;
+    va.B = B; va.X = w.Xd; va.R = w.R; va.P = w.P; va.AP = w.AP; va.Z = w.Z;
+    va.n = a->m; va.k = k; va.part = w.part; va.ticket = a->ticket + 1;
+
+    // x = 0, r = b, ||b||; z = M r, rs_old = r.z, p = z   (sparse_approximate_inverse.hpp:60-94)
+    rc = launch_vec(0, va, cg, max_iters, tol);
+    if (!rc) rc = pcg_m_step(m, va, cg, DOT_PCG_INIT);
+    if (rc) return rc;
+
+    const bool use_graph = getenv("SMLE_NO_GRAPH") == nullptr;
+    if (w.pcg_graph && (w.pcg_m != (const void *)m || w.pcg_epoch_a != a->scratch_epoch || w.pcg_epoch_m != m->scratch_epoch)) {
+        cudaGraphExecDestroy(w.pcg_graph);
+        w.pcg_graph = nullptr;
+    }
+    if (use_graph && !w.pcg_graph) {
+        CgScalars c1 = cg;
+        c1.dot_mode = DOT_PCG_ALPHA;
+        rc = launch_merge<double, true>(a, va.P, va.AP, k, c1, /*dry=*/true);
+        if (!rc) rc = pcg_m_step(m, va, cg, DOT_PCG_BETA, /*dry=*/true);
+        if (rc) return rc;
+        cudaGraph_t graph;
+        CU(cudaStreamBeginCapture(g_stream, cudaStreamCaptureModeThreadLocal));
+        for (int i = 0; i < kGraphIters && !rc; ++i) rc = pcg_iteration(a, m, va, cg);
+        cudaError_t e = cudaStreamEndCapture(g_stream, &graph);
+        g_launches -= 4LL * kGraphIters;
+        if (rc) return rc;
+        if (e != cudaSuccess) return fail(SMLE_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(e));
+        e = cudaGraphInstantiate(&w.pcg_graph, graph, 0);
+        cudaGraphDestroy(graph);
+        if (e != cudaSuccess) return fail(SMLE_ERR_CUDA, "graph instantiate failed: %s", cudaGetErrorString(e));
+        w.pcg_m = m; w.pcg_epoch_a = a->scratch_epoch; w.pcg_epoch_m = m->scratch_epoch;
+    }
+    const int batch = use_graph ? kGraphIters : 4;
+    rc = run_cg_batches(w, max_iters, batch, [&]() -> int {
+        if (use_graph) {
+            CU(cudaGraphLaunch(w.pcg_graph, g_stream));
+            g_launches += 4LL * batch;
+            return SMLE_OK;
+        }
+        for (int i = 0; i < batch; ++i) {
+            int r2 = pcg_iteration(a, m, va, cg);
+            if (r2) return r2;
+        }
+        return SMLE_OK;
+    });
+    if (rc) return rc;
+    const size_t xb = sizeof(double) * w.nk;
+    if (X_dev) CU(cudaMemcpyAsync(X_dev, w.Xd, xb, cudaMemcpyDeviceToDevice, g_stream));
+    if (X_host) CU(cudaMemcpyAsync(X_host, w.Xd, xb, cudaMemcpyDeviceToHost, g_stream));
+    CU(cudaMemcpyAsync(w.ctrl_host, w.ctrl, sizeof(int) * CTRL_WORDS, cudaMemcpyDeviceToHost, g_stream));
+    CU(cudaMemcpyAsync(w.ctrl_host + CTRL_WORDS, cg.last_rel, sizeof(double), cudaMemcpyDeviceToHost, g_stream));
+    CU(cudaStreamSynchronize(g_stream));
+    const int iters = w.ctrl_host[CTRL_ITER];
+    if (iters_out) *iters_out = iters;
+    if (final_rel) memcpy(final_rel, w.ctrl_host + CTRL_WORDS, sizeof(double));
+    if (want_hist) {
+        int nh = iters < w.hist_cap ? iters : w.hist_cap;
+        if (nh > hist_capacity) nh = hist_capacity;
+        CU(cudaMemcpyAsync(hist_out, w.hist, sizeof(double) * (size_t)nh, cudaMemcpyDeviceToHost, g_stream));
+        CU(cudaStreamSynchronize(g_stream));
+        if (hist_len) *hist_len = nh;
+    } else if (hist_len) {
+        *hist_len = 0;
+    }
+    return SMLE_OK;
 }
 
 } // namespace
@@ -1201,7 +1341,7 @@ int smle_csr_tile_coords(smle_csr_t a, int k, int *num_tiles, int *items_per_til
     if (!a || k < 1) return fail(SMLE_ERR_ARG, "bad argument");
     int rc = ensure_init();
     if (rc) return rc;
-    int items = spmv_tile_items();
+    int items = spmv_tile_items(a);
     if (k > 1) {   // the tiling of the SpMM kernel that would run for this (matrix, k)
         int G, VEC;
         if (a->vbytes == 8) pick_shape<double>(k, &G, &VEC); else pick_shape<float>(k, &G, &VEC);
@@ -1301,6 +1441,25 @@ int smle_cg_multi_f64(smle_csr_t a, const double *B, double *X, int k, int max_i
 {
     if (kernel < SMLE_SIMPLE || kernel > SMLE_NONZERO_SPLIT) return fail(SMLE_ERR_ARG, "unknown SpmmKernel %d", kernel);
     return cg_solve(a, B, X, k, max_iters, tol, dev, iters_out, hist, hist_capacity, hist_len, final_rel_res);
+}
+
+int smle_pcg_spai_multi_f64(smle_csr_t a, smle_csr_t m, const double *B, double *X, int k, int max_iters, double tol,
+                            int kernel, int dev, int *iters_out, double *hist, int hist_capacity, int *hist_len,
+                            double *final_rel_res)
+{
+    if (!a || !m || !B || !X || k < 1) return fail(SMLE_ERR_ARG, "smle_pcg_spai: bad argument");
+    if (kernel < SMLE_SIMPLE || kernel > SMLE_NONZERO_SPLIT) return fail(SMLE_ERR_ARG, "unknown SpmmKernel %d", kernel);
+    if (a->vbytes != 8 || m->vbytes != 8) return fail(SMLE_ERR_ARG, "PCG needs fp64 handles");
+    if (a->m != a->n || m->m != a->m || m->n != a->n) return fail(SMLE_ERR_ARG, "A and M must be square and of the same size");
+    int rc = ensure_init();
+    if (rc) return rc;
+    if (dev) return pcg_solve_device(a, m, B, X, nullptr, k, max_iters, tol, iters_out, hist, hist_capacity, hist_len, final_rel_res);
+    rc = ensure_workspace(a, k, 0);
+    if (rc) return rc;
+    CgWorkspace &w = a->ws;
+    if (!w.Bd) CU(cudaMalloc(&w.Bd, sizeof(double) * (w.nk ? w.nk : 1)));
+    CU(cudaMemcpyAsync(w.Bd, B, sizeof(double) * w.nk, cudaMemcpyHostToDevice, g_stream));
+    return pcg_solve_device(a, m, w.Bd, nullptr, X, k, max_iters, tol, iters_out, hist, hist_capacity, hist_len, final_rel_res);
 }
 
 int smle_cg_run_fixed_f64(smle_csr_t a, const double *B, double *X, int k, int iters)

@@ -30,6 +30,7 @@ struct CgVecArgs {
     int n, k;
     double *part;          // [gridDim.x * k] per-CTA partials
     unsigned int *ticket;
+    double *__restrict__ Z = nullptr;   // preconditioned residual z = M r (SPAI-PCG only)
 };
 
 // reduce VEC per-lane partials over the workers of a CTA and publish them for this CTA
@@ -118,7 +119,7 @@ cg_init_kernel(CgVecArgs a, CgScalars cg, int max_iters, double tol, int seq_bas
 // relative residual and latch (no_pretreatment.hpp:133-155), beta (:165-176), rs_old <- rs_new
 // (:179-181), error history, iteration count, stop flag (:157-161 or max_iters).
 // ---------------------------------------------------------------------------------------
-__device__ __forceinline__ void cg_finalize_r(const CgVecArgs &a, const CgScalars &cg, double *s_red, int *s_cnt)
+__device__ __forceinline__ void cg_finalize_r(const CgVecArgs &a, const CgScalars &cg, double *s_red, int *s_cnt, bool pcg = false)
 {
     const int tid = threadIdx.x;
     if (a.k == 1) {
@@ -131,8 +132,10 @@ __device__ __forceinline__ void cg_finalize_r(const CgVecArgs &a, const CgScalar
             int cv = cg.conv[0];
             if (!cv && rel < *cg.tol) { cv = 1; cg.conv[0] = 1; }
             cg.rs_new[0] = rn;
-            cg.beta[0] = cv ? 0.0 : rn / ro;
-            cg.rs_old[0] = rn;
+            if (!pcg) {   // (PCG: beta and rs_old come from r.z, formed by the M step)
+                cg.beta[0] = cv ? 0.0 : rn / ro;
+                cg.rs_old[0] = rn;
+            }
             const int it = cg.ctrl[CTRL_ITER];
             if (cg.hist && it < cg.hist_cap) cg.hist[it] = rel;
             *cg.last_rel = rel;
@@ -154,8 +157,10 @@ __device__ __forceinline__ void cg_finalize_r(const CgVecArgs &a, const CgScalar
         int cv = cg.conv[c];
         if (!cv && rel < tol) { cv = 1; cg.conv[c] = 1; }
         nconv += cv;
-        cg.beta[c] = cv ? 0.0 : rn / ro;
-        cg.rs_old[c] = rn;
+        if (!pcg) {
+            cg.beta[c] = cv ? 0.0 : rn / ro;
+            cg.rs_old[c] = rn;
+        }
     }
     s_red[tid] = worst;
     s_cnt[tid] = nconv;
@@ -260,6 +265,83 @@ cg_update_xp_kernel(CgVecArgs a, CgScalars cg)
                 for (int v = 0; v < VEC; ++v) p[v] = r[v] + be[v] * p[v];
                 st_vec<double, VEC>(a.P + off, p);
             }
+        }
+    }
+}
+
+// =======================================================================================
+// SPAI-preconditioned CG (SPAISolveMultiple, work_2025/main/sparse_approximate_inverse.hpp:31-230).
+// One iteration = SpMM<DOT>(A, P -> AP, alpha) | pcg_update_xr | SpMM<DOT>(M, R -> Z, beta) |
+// pcg_update_p: 2 sparse products + 9 block passes (reference: 2 products + ~16 passes).
+// =======================================================================================
+// X += alpha P; R -= alpha AP; r.r (:129-137).  Last CTA: relative residual, latch, history,
+// iteration count, stop flag (:139-166) -- the convergence test precedes the M step.
+template <int G, int VEC>
+__global__ void __launch_bounds__(kThreads)
+pcg_update_xr_kernel(CgVecArgs a, CgScalars cg)
+{
+    constexpr int W = kThreads / G, KB = G * VEC;
+    __shared__ double s_w[kWarps][KB];
+    __shared__ double s_red[kThreads];
+    __shared__ int s_cnt[kThreads];
+    if (cg.ctrl[CTRL_STOP]) return;
+    const int tid = threadIdx.x, w = tid / G, li = tid % G;
+    const size_t k = (size_t)a.k;
+    for (int cb = 0; cb * KB < a.k; ++cb) {
+        const int c0 = cb * KB + li * VEC;
+        double s[VEC];
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) s[v] = 0;
+        if (c0 < a.k) {
+            double al[VEC];
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) al[v] = cg.alpha[c0 + v];
+            for (int row = blockIdx.x * W + w; row < a.n; row += gridDim.x * W) {
+                size_t off = (size_t)row * k + c0;
+                double x[VEC], p[VEC], r[VEC], ap[VEC];
+                ld_vec<double, VEC>(x, a.X + off);
+                ld_vec<double, VEC>(p, a.P + off);
+                ld_vec<double, VEC>(r, a.R + off);
+                ld_vec<double, VEC>(ap, a.AP + off);
+#pragma unroll
+                for (int v = 0; v < VEC; ++v) {
+                    x[v] += al[v] * p[v];
+                    r[v] += -al[v] * ap[v];
+                    s[v] += r[v] * r[v];
+                }
+                st_vec<double, VEC>(a.X + off, x);
+                st_vec<double, VEC>(a.R + off, r);
+            }
+        }
+        publish_partials<G, VEC>(s, cb, a.k, a.part, s_w);
+    }
+    if (!last_cta_election(a.ticket, gridDim.x)) return;
+    cg_finalize_r(a, cg, s_red, s_cnt, /*pcg=*/true);
+}
+
+// P = Z + beta P (:194).  Skipped once the stop flag is up (the reference breaks before the M step).
+template <int G, int VEC>
+__global__ void __launch_bounds__(kThreads)
+pcg_update_p_kernel(CgVecArgs a, CgScalars cg)
+{
+    constexpr int W = kThreads / G, KB = G * VEC;
+    if (cg.ctrl[CTRL_STOP]) return;
+    const int tid = threadIdx.x, w = tid / G, li = tid % G;
+    const size_t k = (size_t)a.k;
+    for (int cb = 0; cb * KB < a.k; ++cb) {
+        const int c0 = cb * KB + li * VEC;
+        if (c0 >= a.k) continue;
+        double be[VEC];
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) be[v] = cg.beta[c0 + v];
+        for (int row = blockIdx.x * W + w; row < a.n; row += gridDim.x * W) {
+            size_t off = (size_t)row * k + c0;
+            double z[VEC], p[VEC];
+            ld_vec<double, VEC>(z, a.Z + off);
+            ld_vec<double, VEC>(p, a.P + off);
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) p[v] = z[v] + be[v] * p[v];
+            st_vec<double, VEC>(a.P + off, p);
         }
     }
 }

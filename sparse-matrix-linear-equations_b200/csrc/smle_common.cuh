@@ -31,7 +31,38 @@ struct CgScalars {
     double *last_rel;  // max relative residual of the last iteration (1 double)
     int hist_cap;
     double *tol;       // relative tolerance, device resident so CUDA graphs stay valid across calls
+    int dot_mode;      // what the fused dot product of an SpMV / SpMM<DOT> launch becomes (cg_dot_scalars)
 };
+
+// The last CTA of an SpMV / SpMM<DOT> launch turns the fused dot product X[:,c].Y[:,c] into the scalars
+// of the solver that launched it:
+//   0  CG        p.Ap -> alpha = rs_old / pAp, 0 once latched     (no_pretreatment.hpp:107-120)
+//   1  SPAI-PCG  p.Ap -> alpha, also 0 when pAp == 0              (sparse_approximate_inverse.hpp:119-127)
+//   2  SPAI-PCG  r.z with z = M r -> beta = rs_new / rs_old (0 once latched or rs_old == 0),
+//                rs_old <- rs_new                                  (:183-192)
+//   3  SPAI-PCG  initial r.z -> rs_old, beta = 0 (so that p = z + beta p starts as z)  (:88-94)
+enum DotMode { DOT_CG_ALPHA = 0, DOT_PCG_ALPHA = 1, DOT_PCG_BETA = 2, DOT_PCG_INIT = 3 };
+
+__device__ __forceinline__ void cg_dot_scalars(const CgScalars &cg, int c, double dot)
+{
+    const bool latched = cg.conv[c] != 0;
+    if (cg.dot_mode == DOT_CG_ALPHA) {
+        cg.pAp[c] = dot;
+        cg.alpha[c] = latched ? 0.0 : cg.rs_old[c] / dot;
+    } else if (cg.dot_mode == DOT_PCG_ALPHA) {
+        cg.pAp[c] = dot;
+        cg.alpha[c] = (!latched && dot != 0.0) ? cg.rs_old[c] / dot : 0.0;
+    } else if (cg.dot_mode == DOT_PCG_BETA) {
+        const double ro = cg.rs_old[c];
+        cg.rs_new[c] = dot;
+        cg.beta[c] = (!latched && ro != 0.0) ? dot / ro : 0.0;
+        cg.rs_old[c] = dot;
+    } else {
+        cg.rs_new[c] = dot;
+        cg.rs_old[c] = dot;
+        cg.beta[c] = 0.0;
+    }
+}
 
 // ---------------------------------------------------------------------------------------
 // vector load / store of VEC consecutive values (VEC*sizeof(V) in {4, 8, 16} bytes)

@@ -337,7 +337,7 @@ merge_kernel(MergeArgs<V> a, CgScalars cg)
         // pAp[c] then alpha[c] = latched ? 0 : rs_old/pAp  (no_pretreatment.hpp:107-120)
         cta_reduce_columns<V>(a.dot_part, a.fix_part, entries, a.k, (V *)cg.pAp, s_red);
         for (int c = tid; c < a.k; c += kThreads)
-            cg.alpha[c] = cg.conv[c] ? 0.0 : cg.rs_old[c] / cg.pAp[c];
+            cg_dot_scalars(cg, c, (double)cg.pAp[c]);
     }
 }
 

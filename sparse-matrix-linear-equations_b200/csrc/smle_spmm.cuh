@@ -461,7 +461,7 @@ spmm_rows_kernel(SpmmArgs<V> a, CgScalars cg)
         if (!last_cta_election(a.ticket, gridDim.x)) return;
         cta_reduce_columns<V>(a.dot_part, nullptr, gridDim.x, a.k, (V *)cg.pAp, s_red);
         for (int c = tid; c < a.k; c += blockDim.x)
-            cg.alpha[c] = cg.conv[c] ? 0.0 : cg.rs_old[c] / cg.pAp[c];
+            cg_dot_scalars(cg, c, (double)cg.pAp[c]);
     }
 }
 

@@ -574,12 +574,12 @@ spmv_kernel(SpmvArgs<V> a, CgScalars cg)
         // ---- last CTA done: p.Ap from the per-CTA partials in CTA order (deterministic) -------------
         if (!last_cta_election(a.ticket, gridDim.x)) return;
         const V pAp = cta_reduce_one<V>(a.dot_part, nullptr, gridDim.x, s_red);
-        if (tid == 0) cg.pAp[0] = (double)pAp;
         if (a.dist) {
             // this rank's partial -> every rank's mailbox; K2 adds the G partials in rank order
+            if (tid == 0) cg.pAp[0] = (double)pAp;
             dist_post(*a.dist, 0, (double)pAp, cg.ctrl);
         } else if (tid == 0) {
-            cg.alpha[0] = cg.conv[0] ? 0.0 : cg.rs_old[0] / (double)pAp;
+            cg_dot_scalars(cg, 0, (double)pAp);
         }
     }
 }

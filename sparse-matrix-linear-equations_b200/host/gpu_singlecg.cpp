@@ -26,7 +26,8 @@ int main(int argc, char **argv)
     const bool quiet = args.flag("quiet");
     if (gpus < 1 || gpus > smle_multi::kMaxWorld) { fprintf(stderr, "--gpus must be 1..%d\n", smle_multi::kMaxWorld); return 1; }
     // with --gpus the workers bind the devices after the fork: no CUDA call in this process before it
-    if (gpus == 1 && smle_init(device)) smle_adapters::die("smle_init");
+    const bool partitioned = gpus > 1 || args.flag("partitioned");
+    if (!partitioned && smle_init(device)) smle_adapters::die("smle_init");
 
     Csr<double> a;
     std::string label = matrix_from_args(args, a, true);
@@ -43,7 +44,7 @@ int main(int argc, char **argv)
     double threshold = args.flag("raw_tolerance") ? tolerance : smle_driver_threshold_f64(b.data(), (int)n, tolerance);
 
     double min_ms = 0, total_iters = 0;
-    if (gpus == 1 && !args.flag("partitioned")) {
+    if (!partitioned) {
         x_own.resize((size_t)n * L);
         TestGpuCGSolveSingle(a, b.data(), x_own.data(), max_iters, threshold, L, timing_iters, min_ms, total_iters);
     } else {

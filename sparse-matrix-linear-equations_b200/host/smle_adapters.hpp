@@ -13,6 +13,9 @@
 //   GpuCGSolveMultiple   <- CGSolveMultiple        work_2025/main/no_pretreatment.hpp:35-197
 //   TestGpuCGSolveSingle <- TestCGSolveSingle      work_2025/main/single_strategy.hpp:179-240
 //   TestGpuCGMultipleRHS <- TestCGMultipleRHS      work_2025/main/no_pretreatment.hpp:205-256
+//   GpuSparseApproximateInversion <- SparseApproximateInversion  work_2025/cg/sparse_approximate_inversion.hpp:41-321
+//   GpuSPAISolveMultiple <- SPAISolveMultiple     work_2025/main/sparse_approximate_inverse.hpp:31-230
+//   TestGpuCGMultipleSPAI <- TestCGMultipleSPAI   work_2025/main/sparse_approximate_inverse.hpp:232-287
 //
 // The matrix argument is duck-typed: anything with the fields of the reference's
 // CsrMatrix<ValueT,int> (sparse_matrix.h:648-653) works, including the reference type itself, so
@@ -153,6 +156,57 @@ inline int GpuCGSolveMultiple(CsrT &a, const ValueT *B, ValueT *X, int num_vecto
         smle_adapters::die("smle_cg_multi_f64");
     if (max_errors) max_errors->assign(hist.begin(), hist.begin() + hist_len);
     return iters;
+}
+
+// SparseApproximateInversion (work_2025/cg/sparse_approximate_inversion.hpp:41-321): fills `l` with A's
+// pattern and the SPAI values.  `l` must be default-constructed; its arrays are allocated with new[]
+// (the reference's non-MKL branch, :71-75), so CsrMatrix's destructor releases them.
+template <typename CsrT>
+inline bool GpuSparseApproximateInversion(const CsrT &a, CsrT &l)
+{
+    using V = typename std::remove_pointer<decltype(a.values)>::type;
+    using O = typename std::remove_pointer<decltype(a.row_offsets)>::type;
+    static_assert(sizeof(V) == 8, "the reference drivers build SPAI for <double,int> only");
+    l.num_rows = a.num_rows; l.num_cols = a.num_cols; l.num_nonzeros = a.num_nonzeros;
+    l.row_offsets = new O[a.num_rows + 1];
+    l.column_indices = new O[a.num_nonzeros > 0 ? a.num_nonzeros : 1];
+    l.values = new V[a.num_nonzeros > 0 ? a.num_nonzeros : 1];
+    for (long long i = 0; i <= a.num_rows; ++i) l.row_offsets[i] = a.row_offsets[i];
+    for (long long i = 0; i < a.num_nonzeros; ++i) l.column_indices[i] = a.column_indices[i];
+    return smle_spai_build_f64(a.num_rows, a.num_nonzeros, a.row_offsets, a.column_indices, (const double *)a.values,
+                               (double *)l.values) == 0;
+}
+
+// SPAISolveMultiple (work_2025/main/sparse_approximate_inverse.hpp:31-230)
+template <typename ValueT, typename CsrT>
+inline int GpuSPAISolveMultiple(CsrT &a, CsrT &m, const ValueT *B, ValueT *X, int num_vectors, int max_iters, ValueT tolerance,
+                                int kernel_type, std::vector<double> *max_errors = nullptr)
+{
+    static_assert(sizeof(ValueT) == 8, "the reference instantiates the solvers for <double,int> only");
+    int iters = 0, hist_len = 0;
+    std::vector<double> hist(max_errors ? (size_t)(max_iters > 0 ? max_iters : 1) : 0);
+    if (smle_pcg_spai_multi_f64(smle_adapters::handle_of(a), smle_adapters::handle_of(m), B, X, num_vectors, max_iters, tolerance,
+                                kernel_type, 0, &iters, max_errors ? hist.data() : nullptr, (int)hist.size(), &hist_len, nullptr))
+        smle_adapters::die("smle_pcg_spai_multi_f64");
+    if (max_errors) max_errors->assign(hist.begin(), hist.begin() + hist_len);
+    return iters;
+}
+
+// TestCGMultipleSPAI (sparse_approximate_inverse.hpp:232-287): no warm-up solves, min over timed solves
+template <typename ValueT, typename CsrT>
+inline void TestGpuCGMultipleSPAI(CsrT &a, CsrT &m, ValueT *b_vectors, ValueT *x_solutions, int max_iters, ValueT tolerance,
+                                  int num_vectors, int timing_iterations, int kernel_type, double &min_ms,
+                                  double &iters_of_min_ms, std::vector<double> *max_errors = nullptr)
+{
+    min_ms = std::numeric_limits<double>::max();
+    iters_of_min_ms = 0;
+    for (int it = 0; it < timing_iterations; ++it) {
+        auto t0 = std::chrono::steady_clock::now();
+        int iters = GpuSPAISolveMultiple(a, m, b_vectors, x_solutions, num_vectors, max_iters, tolerance, kernel_type,
+                                         it == 0 ? max_errors : nullptr);
+        double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        if (ms < min_ms) { min_ms = ms; iters_of_min_ms = iters; }
+    }
 }
 
 // TestCGSolveSingle: L vectors, vector v = b_vectors[v*n ...] (column-major), solved one after

@@ -270,6 +270,24 @@ class CsrMatrix:
                                        C.byref(hl), C.byref(rel)))
         return it.value, X, (hist[: hl.value].copy() if want_history else None), rel.value
 
+    def pcg_spai_solve_multiple(self, M: "CsrMatrix", B, max_iters: int, tolerance: float, kernel_type: int = MERGE,
+                                out=None, want_history: bool = True):
+        """-> (iterations, X, max_errors, final_rel_res)
+        SPAISolveMultiple (work_2025/main/sparse_approximate_inverse.hpp:31-230); M = handle of the SPAI matrix."""
+        k = int(B.shape[1])
+        pB, dev, kB = _arg(B, np.float64)
+        X = out if out is not None else _empty_like_arg(B, (self.num_rows, k), np.float64)
+        pX, dev_x, kX = _arg(X, np.float64, writable=True)
+        if dev != dev_x:
+            raise SmleError("B and X must both be host or both be device memory")
+        cap = max(int(max_iters), 1) if want_history else 0
+        hist = np.zeros(cap, dtype=np.float64) if want_history else None
+        it, hl, rel = _I(0), _I(0), _D(0)
+        _check(lib().smle_pcg_spai_multi_f64(self._h, M._h, pB, pX, _I(k), _I(max_iters), _D(tolerance), _I(kernel_type),
+                                             _I(dev), C.byref(it), hist.ctypes.data_as(_P) if want_history else None,
+                                             _I(cap), C.byref(hl), C.byref(rel)))
+        return it.value, X, (hist[: hl.value].copy() if want_history else None), rel.value
+
     def cg_run_fixed(self, B, X, iters: int):
         """exactly `iters` iterations on device blocks (measurement helper)."""
         pB, dev, kB = _arg(B, np.float64)
@@ -358,6 +376,18 @@ def gen_rmat(scale, edge_factor=16, a=0.57, b=0.19, c=0.19, seed=42, unit_values
     """R-MAT power-law matrix standing in for the SuiteSparse set (no network here)."""
     return _gen("rmat", (_I(scale), _I(edge_factor)),
                 (_I(scale), _I(edge_factor), _D(a), _D(b), _D(c), C.c_ulonglong(seed), _I(int(unit_values))), dtype)
+
+
+def spai_build(row_offsets, column_indices, values) -> np.ndarray:
+    """values of the SPAI preconditioner on A's pattern (SparseApproximateInversion,
+    work_2025/cg/sparse_approximate_inversion.hpp:41-321); host code."""
+    ro = np.ascontiguousarray(row_offsets, dtype=np.int32)
+    ci = np.ascontiguousarray(column_indices, dtype=np.int32)
+    va = np.ascontiguousarray(values, dtype=np.float64)
+    out = np.zeros(len(ci), dtype=np.float64)
+    _check(lib().smle_spai_build_f64(_I(len(ro) - 1), _I(len(ci)), ro.ctypes.data_as(_P), ci.ctypes.data_as(_P),
+                                     va.ctypes.data_as(_P), out.ctypes.data_as(_P)))
+    return out
 
 
 def gen_rhs_rand(seed: int, count: int) -> np.ndarray:
