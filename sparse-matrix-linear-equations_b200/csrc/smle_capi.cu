@@ -146,6 +146,7 @@ struct Partition {
     int *maxlen = nullptr; // device, num_tiles: longest in-tile row segment
     int max_len = 0;       // max over maxlen[] (host copy): picks the SpMM kernel
     unsigned char *halo = nullptr;   // device, num_tiles: tile gathers halo columns (row-partitioned handles only)
+    int band = -1;                   // window half-width of the band-window SpMM for this tiling (0: none, -1: unknown)
     // structure-aware SpMM tile schedules, keyed by grid size (smle_spmm.cuh); sched == nullptr: none
     struct Sched { int *sched = nullptr, *off = nullptr; };
     std::map<int, Sched> scheds;
@@ -170,6 +171,7 @@ struct smle_csr_s {
     unsigned scratch_epoch = 0;
     int halo_base = -1;               // local block of a row partition: first halo column (else -1)
     int far_stride = -1;              // dominant far column offset in rows (0: none, -1: not probed yet)
+    std::vector<int> common_offsets;  // column offsets > 0 that >= 40 % of the sampled rows have, descending
     CgWorkspace ws;
 };
 
@@ -359,6 +361,7 @@ int far_stride(smle_csr_t a, int *out)
 {
     if (a->far_stride >= 0) { *out = a->far_stride; return SMLE_OK; }
     a->far_stride = 0;
+    a->common_offsets.clear();
     *out = 0;
     if (a->m < 4096 || a->m != a->n) return SMLE_OK;
     const int ns = 2048;
@@ -383,7 +386,10 @@ int far_stride(smle_csr_t a, int *out)
         }
     }
     for (auto it = freq.rbegin(); it != freq.rend(); ++it)
-        if (it->second * 10 >= ns * 4) { a->far_stride = it->first; break; }
+        if (it->second * 10 >= ns * 4) {
+            if (!a->far_stride) a->far_stride = it->first;
+            a->common_offsets.push_back(it->first);   // descending
+        }
     *out = a->far_stride;
     return SMLE_OK;
 }
@@ -516,6 +522,7 @@ int launch_spmm_rows_t(smle_csr_t a, const V *X, V *Y, int k, const CgScalars &c
     args.tile_carry = (V *)a->tile_carry;
     args.dot_part = (V *)a->dot_part;
     args.ticket = a->ticket;
+    args.band = 0;
     static int ypol = -1;
     if (ypol < 0) ypol = env_int("SMLE_SPMM_YPOL", 1);
     args.y_policy = ypol;
@@ -525,6 +532,83 @@ int launch_spmm_rows_t(smle_csr_t a, const V *X, V *Y, int k, const CgScalars &c
     launch_kernel(kern, dim3(grid), dim3(THREADS + 32), smem, args, cg);
     ++g_launches;
     return check_launch("spmm_rows_kernel");
+}
+
+// ---- band-window variant (k = 32 fp64) ----------------------------------------------------------------
+// The ring holds RING dense rows of 256 B next to two stages of 960-item tiles (212 KB in all).  The
+// window half-width is the largest column offset most rows share that still fits: a tile and its
+// successor must both find their windows in the ring, 2*band + rows(t) + rows(t+1) + 2 <= RING.
+constexpr int kSpmmThreads = 960, kSpmmStages = 2, kSpmmUB = 4;   // default configuration of the row-per-worker kernel
+constexpr int kBandRing = 704, kBandTile = 960;
+
+int band_halfwidth(smle_csr_t a, Partition *p, int *band)
+{
+    *band = 0;
+    if (p->band >= 0) { *band = p->band; return SMLE_OK; }
+    p->band = 0;
+    int D = 0;
+    int rc = far_stride(a, &D);
+    if (rc || a->common_offsets.empty()) return rc;
+    std::vector<int2> xy((size_t)p->num_tiles + 1);
+    CU(cudaMemcpyAsync(xy.data(), p->xy, sizeof(int2) * xy.size(), cudaMemcpyDeviceToHost, g_stream));
+    CU(cudaStreamSynchronize(g_stream));
+    int pair_max = 0;
+    for (int t = 0; t + 2 <= p->num_tiles; ++t) pair_max = std::max(pair_max, xy[(size_t)t + 2].x - xy[(size_t)t].x);
+    if (p->num_tiles == 1) pair_max = xy[1].x - xy[0].x;
+    const int cap = (kBandRing - pair_max - 4) / 2;
+    for (int off : a->common_offsets)   // descending
+        if (off <= cap) { p->band = off; break; }
+    if (p->band < 8) p->band = 0;       // a band that narrow is what L1 already catches
+    *band = p->band;
+    return SMLE_OK;
+}
+
+template <bool DOT>
+int launch_spmm_band(smle_csr_t a, const double *X, double *Y, int k, const CgScalars &cg, bool dry, bool *done)
+{
+    using V = double;
+    constexpr int G = 16, VEC = 2, THREADS = 960, STAGES = 2;
+    using SM = SpmmSmem<V, kBandTile>;
+    constexpr size_t smem = SM::STAGE_BYTES * STAGES + (size_t)kBandRing * G * VEC * sizeof(V);
+    auto kern = spmm_rows_kernel<V, G, VEC, 1, kSpmmUB, THREADS, kBandTile, STAGES, 1, DOT, kBandRing>;
+    *done = false;
+    Partition *p;
+    int rc = get_partition(a, kBandTile, &p);
+    if (rc) return rc;
+    if (p->max_len > kSpmmRowsMaxLen) return SMLE_OK;
+    int band = 0;
+    rc = band_halfwidth(a, p, &band);
+    if (rc || band == 0) return rc;
+    rc = ensure_scratch(a, k);
+    if (!rc) rc = ensure_tile_carry<V>(a, (size_t)p->num_tiles * (size_t)k);
+    if (rc) return rc;
+    static bool attr = false;
+    if (!attr) {
+        CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CU(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        attr = true;
+    }
+    *done = true;
+    if (dry) return SMLE_OK;
+    int grid = g_sms;
+    if (grid > p->num_tiles) grid = p->num_tiles;
+    static int chunk = -1;
+    if (chunk < 0) chunk = env_int("SMLE_SPMM_BAND_CHUNK", 16);
+    SpmmArgs<V> args;
+    args.ro = a->ro; args.ci = a->ci; args.va = (const V *)a->va;
+    args.X = X; args.Y = Y; args.tile_xy = p->xy;
+    args.m = a->m; args.nnz = a->nnz; args.k = k;
+    args.num_tiles = p->num_tiles; args.chunk = chunk > 0 ? chunk : 1;
+    args.sched = nullptr; args.sched_off = nullptr;
+    args.tile_carry = (V *)a->tile_carry;
+    args.dot_part = (V *)a->dot_part;
+    args.ticket = a->ticket;
+    args.band = band;
+    args.y_policy = 1;
+    args.dot_late = 1;
+    launch_kernel(kern, dim3(grid), dim3(THREADS + 32), smem, args, cg);
+    ++g_launches;
+    return check_launch("spmm_rows_kernel (band window)");
 }
 
 // <threads>x<tile>x<stages>x<minb>x<ub>x<nv> as one integer
@@ -553,12 +637,20 @@ constexpr int kSpmmTile = 1920, kSpmmTileNarrow = 1440;
 // for a 7-point stencil, 2 stages = 62 KB so the carve-out stays at 64 KB and L1 at 192 KB), dealt
 // round-robin in chunks of 2.  Blocks wider than 32 lanes
 // (k > 32*VEC) give every lane two vectors so that the fused p.Ap still sees all columns.
-constexpr int kSpmmThreads = 960, kSpmmStages = 2, kSpmmUB = 4;
 
 template <typename V, int G, int VEC, bool DOT>
 int launch_spmm_rows(smle_csr_t a, const V *X, V *Y, int k, const CgScalars &cg, bool dry)
 {
     const long long cfg = spmm_cfg();
+    if constexpr (G == 16 && VEC == 2 && sizeof(V) == 8) {
+        static int band_on = -1;
+        if (band_on < 0) band_on = env_int("SMLE_SPMM_BAND", 0);
+        if (band_on && cfg == 0 && k == 32 && a->m == a->n) {
+            bool done = false;
+            int rc = launch_spmm_band<DOT>(a, X, Y, k, cg, dry, &done);
+            if (rc || done) return rc;
+        }
+    }
     if constexpr (G == 16 && VEC == 2 && sizeof(V) == 8) {   // tuning variants (k = 32 fp64 only)
         if (cfg != 0) {
 #define SMLE_CFG(th, tl, st, mb, ub, nv) \

@@ -132,7 +132,14 @@ cg1d_update_xp_kernel(CgVecArgs a, CgScalars cg, DistCtl d, int mode)
     const uint64_t pol_first = make_policy_evict_first(), pol_last = make_policy_evict_last();
     const long long n2 = a.n >> 1;
     const long long stride = (long long)gridDim.x * kThreads;
-    long long i = (long long)blockIdx.x * kThreads + tid;
+    const long long i0 = (long long)blockIdx.x * kThreads + tid, step = stride * kVecUnroll;
+    // This thread's batches in the order 0, last, 1, 2, ...: the first and the last rows of the slab are
+    // what the neighbours need, so both are pushed at the START of the sweep and the system-scope fence at
+    // its end finds those NVLink writes long completed instead of waiting a round trip for the last ones.
+    const long long nb = i0 < n2 ? (n2 - i0 + step - 1) / step : 0;
+    auto batch_start = [&](long long t) { return i0 + (t == 0 ? 0 : (t == 1 ? nb - 1 : t - 1)) * step; };
+    long long i = i0;
+    bool pushed = false;
     double2 x[kVecUnroll], p[kVecUnroll], r[kVecUnroll];
     auto load = [&](long long base) {
 #pragma unroll
@@ -166,7 +173,7 @@ cg1d_update_xp_kernel(CgVecArgs a, CgScalars cg, DistCtl d, int mode)
     if (mode == 0) {
         const bool final_iter = s_final != 0;
         const double al = cg.alpha[0], be = s_beta;
-        while (i < n2) {
+        for (long long t = 0; t < nb; ++t) {
 #pragma unroll
             for (int u = 0; u < kVecUnroll; ++u) {
                 const long long j = i + u * stride;
@@ -183,15 +190,14 @@ cg1d_update_xp_kernel(CgVecArgs a, CgScalars cg, DistCtl d, int mode)
                             for (int g = 0; g < d.npush; ++g) {
                                 const int off = (int)(2 * j) - d.push_lo[g];
                                 double *dst = d.peer_p[d.push_q[g]] + d.send_dst[d.push_q[g]];
-                                if ((unsigned)off < (unsigned)d.push_cnt[g]) dst[off] = p[u].x;
-                                if ((unsigned)(off + 1) < (unsigned)d.push_cnt[g]) dst[off + 1] = p[u].y;
+                                if ((unsigned)off < (unsigned)d.push_cnt[g]) { dst[off] = p[u].x; pushed = true; }
+                                if ((unsigned)(off + 1) < (unsigned)d.push_cnt[g]) { dst[off + 1] = p[u].y; pushed = true; }
                             }
                         }
                     }
                 }
             }
-            i += stride * kVecUnroll;
-            if (i < n2) load(i);
+            if (t + 1 < nb) { i = batch_start(t + 1); load(i); }
         }
         if ((a.n & 1) && blockIdx.x == 0 && tid == 0) {
             const int j = a.n - 1;
@@ -203,11 +209,11 @@ cg1d_update_xp_kernel(CgVecArgs a, CgScalars cg, DistCtl d, int mode)
                 if (d.fused)
                     for (int g = 0; g < d.npush; ++g) {
                         const int off = j - d.push_lo[g];
-                        if ((unsigned)off < (unsigned)d.push_cnt[g]) d.peer_p[d.push_q[g]][d.send_dst[d.push_q[g]] + off] = pn;
+                        if ((unsigned)off < (unsigned)d.push_cnt[g]) { d.peer_p[d.push_q[g]][d.send_dst[d.push_q[g]] + off] = pn; pushed = true; }
                     }
             }
         }
-        if (d.fused && !final_iter) __threadfence_system();   // peer stores ordered before the sequence numbers
+        if (pushed) __threadfence_system();   // this thread's peer stores are ordered before the sequence numbers
     }
     if (!last_cta_election(a.ticket, gridDim.x)) return;
     if (mode == 0 && d.fused && !s_final) {

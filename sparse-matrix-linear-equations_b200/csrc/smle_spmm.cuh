@@ -147,6 +147,7 @@ struct SpmmArgs {
     V *tile_carry;                     // [num_tiles * k] carry slots, sentinel when empty
     V *dot_part;                       // [gridDim.x * k]  (DOT)
     unsigned int *ticket;
+    int band;                          // RING > 0: half-width of the window around the tile's rows kept in the ring
     int y_policy;                      // 1: stream Y with L2 evict-first
     int dot_late;                      // DOT: load X[row,:] after the gathers (1, default) or before them (0).  Kept as a
                                        // run-time switch on purpose: with the early load compiled out ptxas keeps only 2
@@ -187,12 +188,20 @@ __device__ __noinline__ V carry_publish(const int2 *__restrict__ tile_xy, V *til
 //   THREADS     consumer threads (+ one producer warp);  TILE merge items per tile;  STAGES tiles
 //               in flight;  MINB CTAs per SM
 //   DOT         also accumulate X[r,:].Y[r,:] (p.Ap of CG); needs k <= KB (one column block)
-template <typename V, int G, int VEC, int NV, int UB, int THREADS, int TILE, int STAGES, int MINB, bool DOT>
+//   RING        > 0: band-window variant.  The dense rows [first row - band, last row + band] of the tile
+//               being processed live in a shared-memory ring of RING rows that the producer extends with one
+//               bulk copy per tile (consecutive tiles of a chunk overlap in all but the new rows), so the
+//               gathers of columns inside the band -- self, +-1, +-w of a stencil -- are shared-memory
+//               reads and every dense row crosses L2 -> SM once per chunk instead of once per use.
+//               Columns outside the window (+-w^2) keep the L1 path.  Needs k == KB (one column block).
+template <typename V, int G, int VEC, int NV, int UB, int THREADS, int TILE, int STAGES, int MINB, bool DOT, int RING = 0>
 __global__ void __launch_bounds__(THREADS + 32, MINB)
 spmm_rows_kernel(SpmmArgs<V> a, CgScalars cg)
 {
     using SM = SpmmSmem<V, TILE>;
+    constexpr bool BAND = RING > 0;
     static_assert(UB <= 16, "over-read room behind the staged column indices");
+    static_assert(!BAND || NV == 1, "the band-window variant covers one column block with one vector per lane");
     static_assert(THREADS % 32 == 0 && THREADS % G == 0 && G <= 32, "workers tile the consumer warps");
     constexpr int NW = THREADS / 32;
     constexpr int EPV = SM::EPV;
@@ -240,6 +249,10 @@ spmm_rows_kernel(SpmmArgs<V> a, CgScalars cg)
                                        (size_t)SM::VAL_ELEMS * sizeof(V));
     };
     auto stage_hdr = [&](int s) { return reinterpret_cast<int *>(smem_raw + (size_t)s * SM::STAGE_BYTES + SM::HDR_OFFSET); };
+    // band-window variant: the ring of dense rows sits behind the stages; row g of the current chunk is in
+    // slot (g - chunk origin) mod RING, KB values per slot
+    [[maybe_unused]] V *ring = reinterpret_cast<V *>(smem_raw + SM::STAGE_BYTES * STAGES);
+    constexpr unsigned kRingRowBytes = (unsigned)KB * (unsigned)sizeof(V);
 
     if (tid == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(&s_full[s], 1); mbar_init(&s_empty[s], NW); }
@@ -263,12 +276,22 @@ spmm_rows_kernel(SpmmArgs<V> a, CgScalars cg)
         // =============================== producer warp ===========================================
         if (lane == 0) {
             const uint64_t pol_stream = l2_policy_evict_first();
+            [[maybe_unused]] const uint64_t pol_keep = l2_policy_evict_last();
+            [[maybe_unused]] int prev_t = -2, ring_hi = 0, origin = 0;   // band window: last tile, rows loaded so far, chunk origin
             for (int it = 0;; ++it) {
                 const int t = tile_of(it);
                 const int s = it % STAGES;
                 if (it >= STAGES) {
                     mbar_wait(&s_empty[s], (uint32_t)(it / STAGES - 1) & 1u);
                     fence_proxy_async();
+                }
+                if constexpr (BAND) {
+                    // a new chunk reloads the window from slot 0: the tile before it (one stage back) must have
+                    // been consumed as well, or its rows would be overwritten under the consumers
+                    if (it >= 1 && t != prev_t + 1 && t < a.num_tiles) {
+                        mbar_wait(&s_empty[(it - 1) % STAGES], (uint32_t)((it - 1) / STAGES) & 1u);
+                        fence_proxy_async();
+                    }
                 }
                 // The tile's identity travels with its data: the consumers read the header after the wait
                 // on "full" (the arrive below releases these stores) and never touch the schedule or the
@@ -285,7 +308,25 @@ spmm_rows_kernel(SpmmArgs<V> a, CgScalars cg)
                 const uint32_t nb_col = (uint32_t)((hi.y - yc + 3) & ~3) * 4u;
                 const uint32_t nb_val = (uint32_t)((hi.y - yv + EPV - 1) & ~(EPV - 1)) * (uint32_t)sizeof(V);
                 const uint32_t nb_ro = (uint32_t)((hi.x + 2 - rb + 3) & ~3) * 4u;
-                mbar_expect_tx(&s_full[s], nb_col + nb_val + nb_ro);
+                if constexpr (BAND) {
+                    // window of this tile: rows [first - band, last + band]; consecutive tiles only add the new rows
+                    const int last = min(hi.x, a.m - 1);
+                    const int wlo = max(lo.x - a.band, 0), whi = min(last + a.band + 1, a.m);
+                    int ld_lo;
+                    if (t != prev_t + 1) { origin = wlo; ld_lo = wlo; }
+                    else ld_lo = ring_hi;
+                    const int ld_hi = max(whi, ld_lo);
+                    prev_t = t; ring_hi = ld_hi;
+                    hdr[5] = origin + ((wlo - origin) / RING) * RING;   // subtract this, then wrap once: ring slot of a row
+                    hdr[6] = wlo; hdr[7] = whi;
+                    const int len = ld_hi - ld_lo, s0 = (ld_lo - origin) % RING;
+                    const int len0 = min(len, RING - s0), len1 = len - len0;
+                    mbar_expect_tx(&s_full[s], nb_col + nb_val + nb_ro + (uint32_t)len * kRingRowBytes);
+                    if (len0 > 0) tma_load_1d(ring + (size_t)s0 * KB, a.X + (size_t)ld_lo * KB, (uint32_t)len0 * kRingRowBytes, &s_full[s], pol_keep);
+                    if (len1 > 0) tma_load_1d(ring, a.X + (size_t)(ld_lo + len0) * KB, (uint32_t)len1 * kRingRowBytes, &s_full[s], pol_keep);
+                } else {
+                    mbar_expect_tx(&s_full[s], nb_col + nb_val + nb_ro);
+                }
                 if (nb_col) tma_load_1d(stage_col(s), a.ci + yc, nb_col, &s_full[s], pol_stream);
                 if (nb_val) tma_load_1d(stage_val(s), a.va + yv, nb_val, &s_full[s], pol_stream);
                 tma_load_1d(stage_ro(s), a.ro + rb, nb_ro, &s_full[s], pol_stream);
@@ -314,6 +355,14 @@ spmm_rows_kernel(SpmmArgs<V> a, CgScalars cg)
             // Carries: pseudo-row `rows` is the part of row hi.x that lies in this tile (it continues
             // in tile t+1); local row 0 may have begun in tile t-1.  Both sides meet in slot t-1 / t.
             const bool has_in = t > 0 && x0 < a.m;
+            [[maybe_unused]] int ring_sub = 0, wlo = 0, whi = 0;
+            if constexpr (BAND) { ring_sub = hdr[5]; wlo = hdr[6]; whi = hdr[7]; }
+            // ring slot of dense row g (wlo <= g < whi): g - ring_sub, wrapped once
+            [[maybe_unused]] auto ring_row = [&](int g) {
+                int d = g - ring_sub;
+                d -= (d >= RING) ? RING : 0;
+                return reinterpret_cast<const char *>(ring) + (size_t)(unsigned)d * kRingRowBytes;
+            };
 
             // rotate the worker -> row map from tile to tile: with rows % W != 0 the same workers would
             // otherwise take the extra row of every tile
@@ -342,13 +391,59 @@ spmm_rows_kernel(SpmmArgs<V> a, CgScalars cg)
 #pragma unroll
                         for (int v = 0; v < VEC; ++v) acc[q][v] = 0;
                     V xr[NV][VEC];
-                    if constexpr (DOT) {
+                    if constexpr (DOT && !BAND) {
                         if (!is_out && !a.dot_late) {
 #pragma unroll
                             for (int q = 0; q < NV; ++q)
                                 ldg_vec<V, VEC>(xr[q], reinterpret_cast<const V *>(xlane[q] + (size_t)(unsigned)(x0 + i) * kbytes));
                         }
                     }
+                    if constexpr (BAND) {
+                        // columns are sorted: the nonzeros inside the window are one contiguous run [n0, n1)
+                        int n0 = beg0, n1 = end;
+                        while (n0 < end && pc[n0] < wlo) ++n0;
+                        while (n1 > n0 && pc[n1 - 1] >= whi) --n1;
+                        const int nlow = n0 - beg0, nfar = nlow + (end - n1);
+                        auto far_index = [&](int j) { return j < nlow ? beg0 + j : n1 + (j - nlow); };
+                        const unsigned loff = (unsigned)(li * VEC) * (unsigned)sizeof(V);   // (k == KB: coff[0] = li*VEC)
+                        // far columns first: UB gathers in flight while the band is served from shared memory
+                        V xv[UB][VEC];
+                        int zf[UB];
+                        if (nfar > 0) {
+#pragma unroll
+                            for (int u = 0; u < UB; ++u) {
+                                zf[u] = far_index(min(u, nfar - 1));
+                                ldg_vec<V, VEC>(xv[u], reinterpret_cast<const V *>(xlane[0] + (size_t)(unsigned)pc[zf[u]] * kbytes));
+                            }
+                        }
+                        for (int z = n0; z < n1; ++z) {
+                            V xs[VEC];
+                            ld_vec<V, VEC>(xs, reinterpret_cast<const V *>(ring_row(pc[z]) + loff));
+                            const V av = pv[z];
+#pragma unroll
+                            for (int v = 0; v < VEC; ++v) acc[0][v] += av * xs[v];
+                        }
+                        if (nfar > 0) {
+#pragma unroll
+                            for (int u = 0; u < UB; ++u)
+                                if (u < nfar) {
+                                    const V av = pv[zf[u]];
+#pragma unroll
+                                    for (int v = 0; v < VEC; ++v) acc[0][v] += av * xv[u][v];
+                                }
+                            for (int j = UB; j < nfar; ++j) {   // rows with more than UB far columns (rare)
+                                const int z = far_index(j);
+                                V xg[VEC];
+                                ldg_vec<V, VEC>(xg, reinterpret_cast<const V *>(xlane[0] + (size_t)(unsigned)pc[z] * kbytes));
+                                const V av = pv[z];
+#pragma unroll
+                                for (int v = 0; v < VEC; ++v) acc[0][v] += av * xg[v];
+                            }
+                        }
+                        if constexpr (DOT) {
+                            if (!is_out) ld_vec<V, VEC>(xr[0], reinterpret_cast<const V *>(ring_row(x0 + i) + loff));
+                        }
+                    } else
                     for (int beg = beg0; beg < end; beg += UB) {
                         // UB dense rows requested per pass; ptxas keeps about as many loads in flight per
                         // warp as it has scoreboards, the rest of the latency is hidden by the other warps
@@ -373,7 +468,7 @@ spmm_rows_kernel(SpmmArgs<V> a, CgScalars cg)
                                     for (int v = 0; v < VEC; ++v) acc[q][v] += av * xv[u][q][v];
                             }
                     }
-                    if constexpr (DOT) {
+                    if constexpr (DOT && !BAND) {
                         // the row's own dense row was just gathered for the diagonal entry: an L1 hit now,
                         // and it did not occupy one of the few load slots while the gathers were in flight
                         if (!is_out && a.dot_late) {

@@ -210,3 +210,24 @@ def test_rows_kernel_on_skewed_matrices(gpu):
     env = dict(os.environ, SMLE_SPMM_ROWS_MAXLEN="2000000000")
     r = subprocess.run([sys.executable, "-c", ROWS_KERNEL_CHILD, str(ROOT)], env=env, capture_output=True, text=True, timeout=600)
     assert "ROWS_KERNEL_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_spmm_against_all_three_spmmkernel_oracles(gpu, orc, dtype):
+    """SpmmKernel {SIMPLE, MERGE, NONZERO_SPLIT} (work_2025/types.hpp:11-16) are three CPU threading
+    strategies for the same product; on the GPU all three map to the merge-path kernel
+    (include/smle_b200.h).  The one GPU result must agree with each of the three reference kernels --
+    OmpCsrSpmmT (row_splitting.hpp:18-54), OmpMergeCsrmm (merge_based.hpp:49-153),
+    OmpNonzeroSplitCsrmm (nonzero_splitting.hpp:52-150, on a zeroed output: it adds into the last row)."""
+    rng = np.random.default_rng(5)
+    for name, (ro, ci, va) in _matrices(gpu, dtype):
+        m, n = len(ro) - 1, max(len(ro) - 1, int(ci.max()) + 1)
+        a = gpu.CsrMatrix(ro, ci, va, n)
+        for k in (3, 16):
+            X = rng.random((n, k)).astype(dtype)
+            Y = a.spmm(X)
+            for T in (1, 8):
+                for oracle_kernel in (orc.row_split_csrmm, orc.merge_csrmm, orc.nonzero_split_csrmm):
+                    Y_ref = oracle_kernel(T, ro, ci, va, X, k, n)
+                    assert rel_rownorm_err(Y, Y_ref, (ro, ci, va), X) <= TOL[dtype], (name, k, T, oracle_kernel.__name__)
+        a.close()

@@ -34,6 +34,10 @@ for spec in sys.argv[3:] or ["256x1024x2x2@2"]:
     env = dict(os.environ, SWEEP_TAG=spec)
     if spec == "v1":
         env["SMLE_SPMM_V1"] = "1"
+    elif spec.startswith("band"):        # band-window variant (k = 32 fp64), band<chunk>
+        env["SMLE_SPMM_BAND"] = "1"
+        if spec[4:]:
+            env["SMLE_SPMM_BAND_CHUNK"] = spec[4:]
     elif spec in ("sched0", "sched1"):   # default configuration without / with the structure-aware tile schedule
         env["SMLE_SPMM_SCHED"] = spec[-1]
     else:
