@@ -69,8 +69,8 @@ int smle_copy_to_host(void *host_dst, const void *dev_src, unsigned long long by
 /* Page-lock caller-owned host memory for the duration of a series of calls (cudaHostRegister): with
  * pageable buffers the runtime stages every copy and the batch solve below cannot overlap copies
  * with solves.  The adapters register the driver's b / x blocks once, outside the timing loop
- * (the reference allocates them with mkl_malloc, cpu_singlecg.cpp:80-86).  Already-pinned memory is
- * accepted as is. */
+ * (the reference allocates them with mkl_malloc, cpu_singlecg.cpp:80-86).  Returns 0 when the range
+ * was registered, 1 when it already was page-locked (nothing to unregister), < 0 on failure. */
 int smle_host_register(void *host_ptr, unsigned long long bytes);
 int smle_host_unregister(void *host_ptr);
 

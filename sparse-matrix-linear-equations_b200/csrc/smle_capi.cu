@@ -1292,7 +1292,7 @@ int smle_host_register(void *host_ptr, unsigned long long bytes)
     if (rc) return rc;
     if (!host_ptr || !bytes) return SMLE_OK;
     cudaError_t e = cudaHostRegister(host_ptr, bytes, cudaHostRegisterDefault);
-    if (e == cudaErrorHostMemoryAlreadyRegistered) { cudaGetLastError(); return SMLE_OK; }
+    if (e == cudaErrorHostMemoryAlreadyRegistered) { cudaGetLastError(); return 1; }   // already page-locked: nothing to undo
     if (e != cudaSuccess) { cudaGetLastError(); return fail(SMLE_ERR_CUDA, "cudaHostRegister(%llu bytes) failed: %s", bytes, cudaGetErrorString(e)); }
     return SMLE_OK;
 }

@@ -416,7 +416,9 @@ def dist_bounds(row_offsets, world: int) -> np.ndarray:
 
 def host_register(arr) -> None:
     """page-lock a numpy array for overlapped copies (smle_host_register)."""
-    _check(lib().smle_host_register(_P(arr.ctypes.data), C.c_ulonglong(arr.nbytes)))
+    rc = lib().smle_host_register(_P(arr.ctypes.data), C.c_ulonglong(arr.nbytes))
+    if rc < 0:
+        _check(rc)
 
 
 def host_unregister(arr) -> None:
