@@ -593,7 +593,12 @@ int launch_spmm_band(smle_csr_t a, const double *X, double *Y, int k, const CgSc
     int grid = g_sms;
     if (grid > p->num_tiles) grid = p->num_tiles;
     static int chunk = -1;
-    if (chunk < 0) chunk = env_int("SMLE_SPMM_BAND_CHUNK", 16);
+    if (chunk < 0) {
+        chunk = env_int("SMLE_SPMM_BAND_CHUNK", 16);
+        if (env_int("SMLE_DEBUG_DISPATCH", 0))
+            fprintf(stderr, "[smle] spmm k=%d: band-window kernel, band %d rows, ring %d rows, %d tiles of %d items, chunk %d, %zu B smem\n",
+                    k, band, kBandRing, p->num_tiles, kBandTile, chunk, smem);
+    }
     SpmmArgs<V> args;
     args.ro = a->ro; args.ci = a->ci; args.va = (const V *)a->va;
     args.X = X; args.Y = Y; args.tile_xy = p->xy;

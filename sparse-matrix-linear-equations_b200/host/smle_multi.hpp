@@ -9,6 +9,7 @@
 // rank straight into its rows of a shared x block.  Nothing here is on the data path: halo and dot
 // products travel GPU to GPU inside the kernels.
 #pragma once
+#include <omp.h>
 #include <pthread.h>
 #include <signal.h>
 #include <sys/mman.h>
@@ -83,6 +84,10 @@ template <typename CsrT>
                                 double tol, int timing_iterations)
 {
     const int world = ar->world, m = a.num_rows;
+    // The parent generated the matrix with OpenMP: its worker threads do not exist in this forked child,
+    // and a parallel region that tried to wake them would wait forever (libgomp).  Teams of one thread
+    // never touch the inherited pool; the host work left here (planner remap) is small.
+    omp_set_num_threads(1);
     SMLE_MULTI_CHECK(smle_init(rank));
     std::vector<int> bounds((size_t)world + 1);
     SMLE_MULTI_CHECK(smle_dist_bounds(a.row_offsets, m, world, bounds.data()));   // merge-path search on the GPU

@@ -16,8 +16,8 @@ BIN = ROOT / "sparse-matrix-linear-equations_b200" / "bin"
 def _run(name, *flags, cwd=None):
     exe = BIN / name
     assert exe.exists(), f"{exe} not built (run __graft_entry__.build())"
-    r = subprocess.run([str(exe), *flags], capture_output=True, text=True, cwd=cwd, timeout=600)
-    assert r.returncode == 0, r.stderr[-2000:]
+    r = subprocess.run([str(exe), *flags], capture_output=True, text=True, cwd=cwd, timeout=180)
+    assert r.returncode == 0, (r.stdout[-1500:], r.stderr[-2000:])
     return r.stdout
 
 
