@@ -527,7 +527,12 @@ int launch_spmm_rows_t(smle_csr_t a, const V *X, V *Y, int k, const CgScalars &c
     if (ypol < 0) ypol = env_int("SMLE_SPMM_YPOL", 1);
     args.y_policy = ypol;
     static int dot_late = -1;
-    if (dot_late < 0) dot_late = env_int("SMLE_SPMM_DOT_LATE", 1);
+    if (dot_late < 0) {
+        dot_late = env_int("SMLE_SPMM_DOT_LATE", 1);
+        if (env_int("SMLE_DEBUG_DISPATCH", 0))
+            fprintf(stderr, "[smle] spmm k=%d: row-per-worker kernel, %d threads, %d tiles of %d items, chunk %d, grid %d, schedule %s\n",
+                    k, THREADS, p->num_tiles, TILE, chunk, grid, sched ? "chains" : "round-robin");
+    }
     args.dot_late = dot_late;
     launch_kernel(kern, dim3(grid), dim3(THREADS + 32), smem, args, cg);
     ++g_launches;
@@ -552,10 +557,14 @@ int band_halfwidth(smle_csr_t a, Partition *p, int *band)
     std::vector<int2> xy((size_t)p->num_tiles + 1);
     CU(cudaMemcpyAsync(xy.data(), p->xy, sizeof(int2) * xy.size(), cudaMemcpyDeviceToHost, g_stream));
     CU(cudaStreamSynchronize(g_stream));
-    int pair_max = 0;
-    for (int t = 0; t + 2 <= p->num_tiles; ++t) pair_max = std::max(pair_max, xy[(size_t)t + 2].x - xy[(size_t)t].x);
-    if (p->num_tiles == 1) pair_max = xy[1].x - xy[0].x;
-    const int cap = (kBandRing - pair_max - 4) / 2;
+    // rows of two consecutive tiles, 90th percentile: the kernel clamps the window of the few tiles that hold
+    // more (shorter) rows, so the common case decides the band
+    std::vector<int> pair;
+    for (int t = 0; t + 2 <= p->num_tiles; ++t) pair.push_back(xy[(size_t)t + 2].x - xy[(size_t)t].x);
+    if (pair.empty()) pair.push_back(xy[1].x - xy[0].x);
+    std::sort(pair.begin(), pair.end());
+    const int pair_typ = pair[(pair.size() - 1) * 9 / 10];
+    const int cap = (kBandRing - pair_typ - 4) / 2;
     for (int off : a->common_offsets)   // descending
         if (off <= cap) { p->band = off; break; }
     if (p->band < 8) p->band = 0;       // a band that narrow is what L1 already catches

@@ -310,8 +310,13 @@ spmm_rows_kernel(SpmmArgs<V> a, CgScalars cg)
                 const uint32_t nb_ro = (uint32_t)((hi.x + 2 - rb + 3) & ~3) * 4u;
                 if constexpr (BAND) {
                     // window of this tile: rows [first - band, last + band]; consecutive tiles only add the new rows
+                    // A tile and its successor must both find their windows in the ring: the half-width is
+                    // clamped by the rows of this tile together with either neighbour (a few tiles on the
+                    // faces of a grid hold more, shorter rows; their +-w then take the far path)
+                    const int r_prev = hi.x - a.tile_xy[max(t - 1, 0)].x, r_next = a.tile_xy[min(t + 2, a.num_tiles)].x - lo.x;
+                    const int half = max(min(a.band, (RING - 2 - max(r_prev, r_next)) / 2), 0);
                     const int last = min(hi.x, a.m - 1);
-                    const int wlo = max(lo.x - a.band, 0), whi = min(last + a.band + 1, a.m);
+                    const int wlo = max(lo.x - half, 0), whi = min(last + half + 1, a.m);
                     int ld_lo;
                     if (t != prev_t + 1) { origin = wlo; ld_lo = wlo; }
                     else ld_lo = ring_hi;

@@ -25,11 +25,17 @@ int run(const Args &args, bool quiet)
     if (iters < 0) iters = std::min(200000ll, std::max(100ll, (16ll << 30) / std::max(1, a.num_nonzeros)));
 
     std::vector<V> x((size_t)a.num_cols, V(0.0019)), y((size_t)a.num_rows), gold((size_t)a.num_rows);   // cpu_spmv.cpp:855
+    std::vector<double> scale((size_t)a.num_rows);
     for (int r = 0; r < a.num_rows; ++r) {   // SpmvGold (cpu_spmv.cpp:245-265), alpha = 1, beta = 0
         V s = 0;
-        for (int z = a.row_offsets[r]; z < a.row_offsets[r + 1]; ++z) s += a.values[z] * x[a.column_indices[z]];
+        double mag = 0;
+        for (int z = a.row_offsets[r]; z < a.row_offsets[r + 1]; ++z) {
+            s += a.values[z] * x[a.column_indices[z]];
+            mag += fabs((double)a.values[z] * (double)x[a.column_indices[z]]);
+        }
         gold[r] = s;
-    }
+        scale[r] = mag;   // (|A||x|)_r: what a different summation order is measured against -- on a Poisson
+    }                     // matrix with constant x the interior rows cancel to exactly 0 in the gold order only
 
     auto t0 = std::chrono::steady_clock::now();
     smle_csr_t h = smle_adapters::handle_of(a);
@@ -39,11 +45,11 @@ int run(const Args &args, bool quiet)
     GpuMergeCsrmv<V, int>(0, a, a.row_offsets + 1, a.column_indices, a.values, x.data(), y.data());
     double worst = 0;
     for (int r = 0; r < a.num_rows; ++r) {
-        double d = fabs((double)y[r] - (double)gold[r]) / std::max(1e-300, fabs((double)gold[r]));
+        double d = fabs((double)y[r] - (double)gold[r]) / std::max(1e-300, scale[r]);
         worst = std::max(worst, d);
     }
-    if (!quiet) printf("\tMerge CsrMV (B200): max relative difference vs SpmvGold %.3e  %s\n", worst,
-                       worst < (sizeof(V) == 8 ? 1e-10 : 1e-3) ? "PASS" : "FAIL");
+    if (!quiet) printf("\tMerge CsrMV (B200): max row-scaled difference vs SpmvGold %.3e  %s\n", worst,
+                       worst < (sizeof(V) == 8 ? 1e-12 : 1e-5) ? "PASS" : "FAIL");
 
     // timing with device-resident vectors: `iters` warm runs, `iters` timed runs (cpu_spmv.cpp:458-474)
     void *dx = nullptr, *dy = nullptr;

@@ -47,3 +47,6 @@ for spec in sys.argv[3:] or ["256x1024x2x2@2"]:
             env["SMLE_SPMM_CHUNK"] = chunk
     r = subprocess.run([sys.executable, "-c", CHILD, w, k], env=env, capture_output=True, text=True)
     print(r.stdout.strip() or r.stderr.strip()[-600:], flush=True)
+    for line in r.stderr.splitlines():
+        if line.startswith("[smle]"):
+            print("    " + line, flush=True)
