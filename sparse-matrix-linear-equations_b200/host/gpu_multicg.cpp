@@ -7,22 +7,28 @@
 // --sweep reproduces the missing cpu_multicg2 (Makefile:191, eval_gflops.sh:61-66): kernels
 // {SIMPLE,MERGE,NONZERO_SPLIT} x num_vectors {2,...,128}, CSV
 // matrix_name,kernel,num_vectors,min_ms,gflops,iterations (verification/gflops/gflop_analyze.py).
+// --gpus=N shards the num_vectors columns over N GPUs (one forked worker per GPU, A replicated; the block's
+// iteration count and error history follow from the shards' -- smle_multi.hpp).
 #include "smle_adapters.hpp"
 #include "smle_host.hpp"
+#include "smle_multi.hpp"
 
 using namespace smle_host;
 
 int main(int argc, char **argv)
 {
     Args args(argc, argv);
-    int max_iters = 50000, k = 16, device = 0, timing_iters = -1;
+    int max_iters = 50000, k = 16, device = 0, timing_iters = -1, gpus = 1;
     unsigned seed = 42;
     double tolerance = 1.0e-5;
     std::string output_csv;
     args.get("max_iters", max_iters); args.get("tolerance", tolerance); args.get("num_vectors", k);
     args.get("device", device); args.get("seed", seed); args.get("timing_iters", timing_iters); args.get("output", output_csv);
+    args.get("gpus", gpus);
     const bool quiet = args.flag("quiet");
-    if (smle_init(device)) smle_adapters::die("smle_init");
+    if (gpus < 1 || gpus > smle_multi::kMaxWorld) { fprintf(stderr, "--gpus must be 1..%d\n", smle_multi::kMaxWorld); return 1; }
+    // with --gpus > 1 the workers bind the devices after the fork: no CUDA call in this process
+    if (gpus == 1 && smle_init(device)) smle_adapters::die("smle_init");
 
     Csr<double> a;
     std::string label = matrix_from_args(args, a, true);
@@ -39,7 +45,27 @@ int main(int argc, char **argv)
         smle_gen_rhs_rand_f64(seed, n * kk, B.data());
         double threshold = args.flag("raw_tolerance") ? tolerance : smle_driver_threshold_f64(B.data(), (int)n, tolerance);   // :168
         if (!quiet) printf("Convergence threshold: %.6e\n", threshold);
-        TestGpuCGMultipleRHS(a, B.data(), X.data(), max_iters, threshold, kk, titers, kernel, min_ms, iters, errs);
+        if (gpus == 1) {
+            TestGpuCGMultipleRHS(a, B.data(), X.data(), max_iters, threshold, kk, titers, kernel, min_ms, iters, errs);
+            return;
+        }
+        double *Xs = (double *)smle_multi::shared_alloc(sizeof(double) * (size_t)n * kk);
+        smle_multi::Arena *ar = smle_multi::arena_create(gpus, 16);
+        smle_multi::ColumnShards *cs = smle_multi::column_shards_create(gpus, max_iters);
+        if (smle_multi::run_workers(ar, [&](int rank) {
+                smle_multi::worker_columns(ar, cs, rank, a, B.data(), Xs, kk, max_iters, threshold, titers, kernel);
+            })) { fprintf(stderr, "a worker failed\n"); exit(1); }
+        iters = smle_multi::merge_column_shards(cs, gpus, errs);
+        min_ms = cs->min_ms;
+        if (args.flag("check")) {   // true residual of column 0 on the host (reporting aid)
+            double rr = 0, bb = 0;
+            for (int r = 0; r < a.num_rows; ++r) {
+                double s = 0;
+                for (int z = a.row_offsets[r]; z < a.row_offsets[r + 1]; ++z) s += a.values[z] * Xs[(size_t)a.column_indices[z] * kk];
+                rr += (B[(size_t)r * kk] - s) * (B[(size_t)r * kk] - s); bb += B[(size_t)r * kk] * B[(size_t)r * kk];
+            }
+            printf("  true residual of column 0: %.3e\n", sqrt(rr / bb));
+        }
     };
 
     if (args.flag("sweep")) {

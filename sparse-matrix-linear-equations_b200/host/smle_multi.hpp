@@ -147,6 +147,100 @@ template <typename CsrT>
     _exit(0);
 }
 
+// ---- column-sharded multi-RHS CG (first row) --------------------------------------
+// The k recurrences of CGSolveMultiple never interact: rank g solves columns [lo, hi) of the row-major
+// n x k blocks with A replicated on its GPU.  What the reference returns for the whole block follows
+// from the shards: it iterates until EVERY column has latched (the slowest shard's count), and a shard
+// that has stopped is frozen, so it keeps contributing its final residual to the per-iteration maximum.
+struct ColumnShards {
+    int iters[kMaxWorld];
+    int hist_len[kMaxWorld];
+    double min_ms;
+    double *hist;        // world x hist_cap (shared mapping)
+    int hist_cap;
+};
+
+inline void shard_columns(int k, int rank, int world, int *lo, int *hi)
+{
+    const int base = k / world, extra = k % world;
+    *lo = rank * base + (rank < extra ? rank : extra);
+    *hi = *lo + base + (rank < extra ? 1 : 0);
+}
+
+inline ColumnShards *column_shards_create(int world, int max_iters)
+{
+    ColumnShards *c = (ColumnShards *)shared_alloc(sizeof(ColumnShards));
+    memset(c, 0, sizeof(ColumnShards));
+    c->hist_cap = max_iters > 0 ? max_iters : 1;
+    c->hist = (double *)shared_alloc(sizeof(double) * (size_t)world * (size_t)c->hist_cap);
+    return c;
+}
+
+// -> iterations of the whole block; hist (optional) receives the per-iteration maximum over all columns
+inline int merge_column_shards(const ColumnShards *c, int world, std::vector<double> *hist)
+{
+    int iters = 0;
+    for (int r = 0; r < world; ++r) iters = c->iters[r] > iters ? c->iters[r] : iters;
+    if (hist) {
+        hist->assign((size_t)iters, 0.0);
+        for (int r = 0; r < world; ++r) {
+            const double *h = c->hist + (size_t)r * (size_t)c->hist_cap;
+            const int len = c->hist_len[r];
+            if (len <= 0) continue;
+            for (int i = 0; i < iters; ++i) {
+                const double v = h[i < len ? i : len - 1];
+                if (v > (*hist)[(size_t)i]) (*hist)[(size_t)i] = v;
+            }
+        }
+    }
+    return iters;
+}
+
+// This rank's share of TestCGMultipleRHS (no_pretreatment.hpp:205-256): timing_iterations warm-up solves,
+// then timed ones (min wall time, closed by the slowest rank); B and X are the WHOLE row-major n x k blocks
+// (B inherited from the parent, X a shared mapping), of which the rank packs / fills its columns.
+template <typename CsrT>
+[[noreturn]] inline void worker_columns(Arena *ar, ColumnShards *cs, int rank, const CsrT &a, const double *B, double *X, int k,
+                                        int max_iters, double tol, int timing_iterations, int kernel_type)
+{
+    const int world = ar->world;
+    omp_set_num_threads(1);   // see worker(): no OpenMP teams in a forked child
+    SMLE_MULTI_CHECK(smle_init(rank));
+    int lo, hi;
+    shard_columns(k, rank, world, &lo, &hi);
+    const int kl = hi - lo;
+    const size_t n = (size_t)a.num_rows;
+    cs->iters[rank] = 0; cs->hist_len[rank] = 0;
+    if (kl > 0) {
+        smle_csr_t h = nullptr;
+        SMLE_MULTI_CHECK(smle_csr_create_f64(&h, a.num_rows, a.num_cols, a.num_nonzeros, a.row_offsets, a.column_indices, a.values));
+        std::vector<double> Bl(n * (size_t)kl), Xl(n * (size_t)kl);
+        for (size_t r = 0; r < n; ++r)
+            for (int c = 0; c < kl; ++c) Bl[r * (size_t)kl + c] = B[r * (size_t)k + lo + c];
+        double *hist = cs->hist + (size_t)rank * (size_t)cs->hist_cap;
+        double min_ms = 1e300;
+        for (int t = 0; t < 2 * timing_iterations; ++t) {   // warm-ups, then timed solves
+            sync(ar);
+            auto t0 = std::chrono::steady_clock::now();
+            int it = 0, hl = 0;
+            SMLE_MULTI_CHECK(smle_cg_multi_f64(h, Bl.data(), Xl.data(), kl, max_iters, tol, kernel_type, 0, &it, hist, cs->hist_cap, &hl, nullptr));
+            sync(ar);
+            const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+            if (t >= timing_iterations && ms < min_ms) min_ms = ms;
+            cs->iters[rank] = it; cs->hist_len[rank] = hl;
+        }
+        if (rank == 0) cs->min_ms = min_ms;
+        for (size_t r = 0; r < n; ++r)
+            for (int c = 0; c < kl; ++c) X[r * (size_t)k + lo + c] = Xl[r * (size_t)kl + c];
+        smle_csr_destroy(h);
+    } else {
+        for (int t = 0; t < 2 * timing_iterations; ++t) { sync(ar); sync(ar); }
+    }
+    sync(ar);
+    fflush(stdout);
+    _exit(0);
+}
+
 // Parent side: fork `world` workers running fn(rank), wait for them; if one fails the others are
 // killed (they may be waiting for it at the barrier).  Returns 0 when every worker exited 0.
 template <typename Fn>

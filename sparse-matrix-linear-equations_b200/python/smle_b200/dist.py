@@ -262,3 +262,41 @@ class RowPartitionedCsr:
         us = _D(0)
         capi._check(capi.lib().smle_dist_allreduce_bench_f64(self._h, _I(iters), C.byref(us)))
         return us.value
+
+
+# ---------------------------------------------------------------------------------------------
+# column-sharded multi-RHS CG (first row): the k recurrences of CGSolveMultiple
+# never interact, so rank g solves columns [g*k/G, (g+1)*k/G) with A replicated; what the reference
+# returns for the whole block follows from the shards' results alone
+# ---------------------------------------------------------------------------------------------
+def shard_columns(k: int, rank: int, world: int):
+    """columns [lo, hi) of rank `rank` (equal shares, the first k % world ranks take one more)"""
+    base, extra = divmod(k, world)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def merge_sharded_results(results):
+    """results: per rank (iterations, max_error_history) of CGSolveMultiple on its columns.
+    -> (iterations, history) of the reference's lock-step solve of the whole block
+    (no_pretreatment.hpp:133-161): it stops when EVERY column has latched, i.e. after the slowest shard's
+    count; a shard that has stopped is frozen (alpha = beta = 0), so its columns keep contributing their
+    final relative residual to the per-iteration maximum."""
+    iters = max(r[0] for r in results)
+    hist = np.zeros(iters, dtype=np.float64)
+    for it, h in results:
+        h = np.asarray(h, dtype=np.float64)
+        if len(h) == 0:
+            continue
+        ext = np.concatenate([h[:iters], np.full(max(iters - len(h), 0), h[-1])])
+        hist = np.maximum(hist, ext)
+    return iters, hist
+
+
+def cg_solve_multiple_column_sharded(a, B_local, max_iters: int, tolerance: float, all_gather_object, kernel_type: int = capi.MERGE):
+    """One rank's part of the column-sharded CGSolveMultiple: `a` is this rank's (replicated) CsrMatrix handle,
+    B_local its n x k_local columns.  -> (iterations of the whole block, X_local, history of the whole block).
+    The only communication is one all-gather of (iterations, history) at the end."""
+    it, X, hist, rel = a.cg_solve_multiple(B_local, max_iters, tolerance, kernel_type)
+    iters, hist_all = merge_sharded_results(all_gather_object((it, hist)))
+    return iters, X, hist_all

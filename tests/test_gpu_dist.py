@@ -135,3 +135,63 @@ def test_world1_partition_is_the_plain_solver(gpu, orc):
     it2, x2, _ = A.cg_solve_single(b, 10000, 1e-8)
     assert it2 == it and np.array_equal(x2, x.cpu().numpy())
     A.close()
+
+
+def _sharded_worker(rank, world, port, q):
+    sys.path.insert(0, str(ROOT))
+    sys.path.insert(0, str(ROOT / "sparse-matrix-linear-equations_b200" / "python"))
+    import torch
+    import torch.distributed as dist
+    import smle_b200 as S
+    from smle_b200 import dist as D
+    from oracle import oracle as O
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.cuda.set_device(rank)
+    S.init(rank)
+
+    def gather(obj):
+        out = [None] * world
+        dist.all_gather_object(out, obj)
+        return out
+
+    orc = O.port()
+    ro, ci, va = S.gen_grid3d(20, True, 6.0, -1.0)
+    n, k = len(ro) - 1, 8
+    B = S.gen_rhs_rand(42, n * k).reshape(n, k).copy()
+    B[:, 5] *= 1e-4                                  # one column converges much earlier than the rest
+    lo, hi = D.shard_columns(k, rank, world)
+    a = S.CsrMatrix(ro, ci, va)                      # A replicated
+    iters, X, hist = D.cg_solve_multiple_column_sharded(a, np.ascontiguousarray(B[:, lo:hi]), 10000, 1e-8, gather)
+    it_o, X_o, hist_o = orc.cg_multi(ro, ci, va, B, k, 10000, 1e-8, O.MERGE, 8)
+    nh = min(len(hist), len(hist_o)) - 2
+    ok = abs(iters - it_o) <= max(1, round(0.02 * it_o)) and abs(len(hist) - len(hist_o)) <= 1 \
+        and np.allclose(hist[:nh], hist_o[:nh], rtol=1e-5) and np.allclose(X, X_o[:, lo:hi], rtol=1e-6, atol=1e-9)
+    q.put((rank, bool(ok), iters, it_o))
+    a.close()
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_column_sharded_multi_rhs_cg(gpu):
+    """SURVEY.md section 8e, first row: columns of the k right-hand sides over 2 GPUs, A replicated; iteration count
+    and error history of the whole block from one gather, against CGSolveMultiple's restatement on all k columns."""
+    if gpu.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_sharded_worker, args=(r, 2, 29790, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    try:
+        res = sorted(q.get(timeout=300) for _ in range(2))
+    finally:
+        for p in procs:
+            p.join(timeout=60)
+            if p.is_alive():
+                p.kill()
+    assert all(p.exitcode == 0 for p in procs)
+    assert all(r[1] for r in res), res
+    assert res[0][2] == res[1][2]

@@ -139,3 +139,23 @@ def test_gpu_singlecg_partitioned_flag_on_one_gpu(gpu, tmp_path):
     out = _run("gpu_singlecg", "--grid3d=16", "--num_vectors=2", "--partitioned", "--check", f"--output={tmp_path}/r1.csv")
     assert "row partition over 1 GPU(s): [0,4096) halo 0" in out
     assert re.search(r"method=SINGLE_LOOP: [\d.]+ ms, (\d+) iters", out)
+
+
+def test_gpu_multicg_columns_sharded_over_two_gpus(gpu, orc, tmp_path):
+    """--gpus=2: the num_vectors columns split over two forked workers (A replicated); iteration count and error
+    history of the whole block are merged from the shards (host/smle_multi.hpp)."""
+    if gpu.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    (tmp_path / "data" / "error_data").mkdir(parents=True)
+    out = _run("gpu_multicg", "--grid3d=20", "--num_vectors=6", "--timing_iters=1", "--gpus=2", "--check", cwd=tmp_path)
+    iters = float(re.search(r"Iters:\s+([\d.]+)", out).group(1))
+    ro, ci, va = orc.gen_grid3d(20, True, 6.0, -1.0)
+    n = len(ro) - 1
+    B = orc.rhs_rand(42, n * 6).reshape(n, 6)
+    thr = orc.driver_threshold(B.ravel(), n, 1e-5)
+    want, _, hist = orc.cg_multi(ro, ci, va, B, 6, 50000, thr, O.NONZERO_SPLIT, 8)
+    assert abs(iters - want) <= max(1, round(0.02 * want))
+    lines = (tmp_path / "data" / "error_data" / "grid3d_20_cg_errors.csv").read_text().splitlines()
+    assert len(lines) - 1 == int(iters)
+    np.testing.assert_allclose([float(l.split(",")[1]) for l in lines[1:6]], hist[:5], rtol=1e-5)
+    assert float(re.search(r"true residual of column 0: ([\d.e+-]+)", out).group(1)) < thr * 1.01
