@@ -130,6 +130,8 @@ struct SpmvSmem {
 constexpr int kRowPathMaxLen = 32;
 // longest row segment one warp reduces by itself; longer ones are strided over by the whole CTA
 constexpr int kWarpRowMax = 1024;
+// capacity of the per-tile queue of such segments (a tile of 3840 nonzeros holds at most 116 rows longer than 32)
+constexpr int kLongCap = 128;
 
 // One warp per tile: the longest run of nonzeros of a single row inside the tile (complete rows,
 // the leading part of row x0 and the trailing part of row x1).  A property of the matrix and the
@@ -303,6 +305,7 @@ spmv_kernel(SpmvArgs<V> a, CgScalars cg)
     __shared__ uint64_t s_full[STAGES], s_empty[STAGES];
     __shared__ V s_wsum[NW];
     __shared__ int s_huge[4], s_nhuge;       // row segments longer than kWarpRowMax in the current tile
+    __shared__ int s_long[3][kLongCap], s_nlong[3], s_next[3];   // queued segments of 33..kWarpRowMax (balance mode)
     __shared__ V s_tcarry[kChainTiles];      // carry-out of each tile of the current chunk
     __shared__ int s_trow[kChainTiles];      // first row of the tile, or -1 when no row completes in it
     __shared__ V s_running;                  // carry chained so far (row in progress at the chunk start)
@@ -338,6 +341,7 @@ spmv_kernel(SpmvArgs<V> a, CgScalars cg)
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         s_running = 0;
         s_nhuge = 0;
+        for (int q = 0; q < 3; ++q) { s_nlong[q] = 0; s_next[q] = 0; }
     }
     __syncthreads();
 
@@ -380,6 +384,7 @@ spmv_kernel(SpmvArgs<V> a, CgScalars cg)
         // kernel until it has completed.
         if constexpr (DOT) { griddep_wait(); griddep_launch_dependents(); }
         bool halo_ready = false;
+        int gen_count = 0;   // general tiles processed by this CTA so far (same in every thread)
         for (int t = t0; t < t1; ++t) {
             const int it = t - t0, s = it % STAGES, slot = it % kChainTiles;
             const uint32_t parity = (uint32_t)(it / STAGES) & 1u;
@@ -445,6 +450,15 @@ spmv_kernel(SpmvArgs<V> a, CgScalars cg)
                         s_tcarry[slot] = sum;
                     }
                 };
+                // balance (debug_flags bit 1): segments of 33..kWarpRowMax are not reduced by the warp that found
+                // them but queued and dealt to the warps dynamically after one barrier -- on power-law matrices
+                // a few such rows per tile otherwise keep one warp busy while 14 wait for the stage to drain.
+                // Queue counters are triple-buffered over the general tiles of this CTA: the set for the NEXT
+                // general tile is re-armed before this tile's barrier, when its last users are two barriers behind.
+                const bool balance = (a.debug_flags & 2) != 0;
+                const int qc = gen_count % 3, qn = (gen_count + 1) % 3;
+                ++gen_count;
+                if (balance && tid == 0) { s_nlong[qn] = 0; s_next[qn] = 0; }
                 auto tiers = [&](auto coh) {
                     constexpr bool COH = decltype(coh)::value;
                     for (int base = 0; base <= rows; base += THREADS) {   // warp-uniform trip count (ballots inside)
@@ -458,7 +472,9 @@ spmv_kernel(SpmvArgs<V> a, CgScalars cg)
                         const int len = end - beg;
                         V sum = 0;
                         if (valid && len <= kRowPathMaxLen) sum = row_sum<V, COH>(a.x, pc, pv, beg, end);
-                        unsigned med = __ballot_sync(0xffffffffu, valid && len > kRowPathMaxLen && len <= kWarpRowMax);
+                        const bool is_med = valid && len > kRowPathMaxLen && len <= kWarpRowMax;
+                        if (balance && is_med) s_long[qc][atomicAdd(&s_nlong[qc], 1) & (kLongCap - 1)] = i;
+                        unsigned med = __ballot_sync(0xffffffffu, is_med && !balance);
                         while (med) {
                             const int src = __ffs(med) - 1;
                             med &= med - 1;
@@ -469,10 +485,26 @@ spmv_kernel(SpmvArgs<V> a, CgScalars cg)
                             if (lane == src) sum = part;
                         }
                         if (valid && len > kWarpRowMax) s_huge[atomicAdd(&s_nhuge, 1) & 3] = i;
-                        else if (valid) emit(i, sum);
+                        else if (valid && !(balance && is_med)) emit(i, sum);
                     }
-                    if (tile_ml > kWarpRowMax) {   // uniform over the CTA: the tile's longest segment is known
-                        consumer_sync<THREADS>();
+                    if (balance || tile_ml > kWarpRowMax) consumer_sync<THREADS>();   // queues complete (uniform over the CTA)
+                    if (balance) {
+                        const int nl = min(s_nlong[qc], kLongCap);
+                        for (;;) {
+                            int idx = 0;
+                            if (lane == 0) idx = atomicAdd(&s_next[qc], 1);
+                            idx = __shfl_sync(0xffffffffu, idx, 0);
+                            if (idx >= nl) break;
+                            const int i = s_long[qc][idx];
+                            const int beg = (i == 0) ? 0 : s_re[i - 1] - y0;
+                            const int end = (i == rows) ? nz : s_re[i] - y0;
+                            V part = strided_sum<V, COH, 32>(a.x, pc, pv, beg, end, lane);
+#pragma unroll
+                            for (int d = 16; d > 0; d >>= 1) part += __shfl_xor_sync(0xffffffffu, part, d);
+                            if (lane == 0) emit(i, part);
+                        }
+                    }
+                    if (tile_ml > kWarpRowMax) {   // the tile's longest segment is known: uniform over the CTA
                         const int nh = min(s_nhuge, 4);
                         for (int h = 0; h < nh; ++h) {
                             const int i = s_huge[h];
