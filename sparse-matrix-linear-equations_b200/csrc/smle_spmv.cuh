@@ -13,10 +13,11 @@
 //   * regular tiles (no row segment longer than 32, every stencil): one thread per row straight from
 //     the stage buffers -- adjacent lanes own adjacent rows, so a warp's gathers of x fall into 2-3
 //     cache lines and y is written coalesced; no CTA-wide barrier, warps drift across tiles;
-//   * general tiles (R-MAT hubs, the wheel's spoke row): the same pass, plus a warp-private reduction
-//     for rows of 33..1024 nonzeros (lanes stride over the row, shuffle tree) and a CTA-wide strided
-//     reduction for the rare longer segment (at most two per tile) -- the only barriers on the
-//     data path; the classic per-thread merge walk with its three barriers per tile is gone;
+//   * general tiles (R-MAT hubs, the wheel's spoke row): the same pass for the short rows; rows of
+//     33..1024 nonzeros are queued and dealt to the warps dynamically (lanes stride over the row,
+//     shuffle tree; one barrier per such tile), the rare longer segment (at most two per tile) is
+//     reduced by the whole CTA; the classic per-thread merge walk with its three barriers per tile
+//     and its bank conflicts is gone;
 //   * carries: per-tile -> per-CTA in shared memory; the row cut by a CTA boundary is finished
 //     wait-free through one global slot per boundary (the party that arrives second adds owner
 //     part + carry, merge_based.hpp:137-149 semantics), so a plain SpMV has no last-CTA epilogue;
@@ -285,7 +286,7 @@ __device__ __noinline__ void cta_carry_publish(const int2 *__restrict__ tile_xy,
 //       wait "full" -> thread-per-row gather + FMA straight from the stage buffers -> arrive
 //       on "empty".  NO CTA-wide barrier: warps drift freely across tiles.
 //   consumers, general tile (long or wildly uneven rows): the same pass; rows of 33..1024 nonzeros
-//       are reduced by the warp that found them, longer segments by the whole CTA.
+//       are queued and dealt to the warps after one barrier, longer segments go to the whole CTA.
 //   carries: every tile records (first row, has-complete-row, carry-out) in shared memory;
 //       thread 0 chains them in tile order every kChainTiles tiles and the fix-ups are applied
 //       in parallel (reference semantics: merge_based.hpp:137-149, carry added after the row's
@@ -450,12 +451,14 @@ spmv_kernel(SpmvArgs<V> a, CgScalars cg)
                         s_tcarry[slot] = sum;
                     }
                 };
-                // balance (debug_flags bit 1): segments of 33..kWarpRowMax are not reduced by the warp that found
-                // them but queued and dealt to the warps dynamically after one barrier -- on power-law matrices
-                // a few such rows per tile otherwise keep one warp busy while 14 wait for the stage to drain.
-                // Queue counters are triple-buffered over the general tiles of this CTA: the set for the NEXT
-                // general tile is re-armed before this tile's barrier, when its last users are two barriers behind.
-                const bool balance = (a.debug_flags & 2) != 0;
+                // Segments of 33..kWarpRowMax are not reduced by the warp that found them but queued and dealt to
+                // the warps dynamically after one barrier: on power-law matrices a few such rows per tile
+                // otherwise keep one warp busy while 14 wait for the stage to drain (R-MAT scale 22 / 23:
+                // 1007 -> 628 us, 2009 -> 1377 us; profiles/r02_spmv_general_tile_balance_ab.txt; debug_flags
+                // bit 1 switches back to the warp-private reduction).  Queue counters are triple-buffered over
+                // the general tiles of this CTA: the set for the NEXT general tile is re-armed before this
+                // tile's barrier, when its last users are two barriers behind.
+                const bool balance = (a.debug_flags & 2) == 0;
                 const int qc = gen_count % 3, qn = (gen_count + 1) % 3;
                 ++gen_count;
                 if (balance && tid == 0) { s_nlong[qn] = 0; s_next[qn] = 0; }
