@@ -752,6 +752,7 @@ int launch_spmv_t(smle_csr_t a, const V *x, V *y, const CgScalars &cg, bool dry)
     args.dist = (const DistCtl *)g_spmv_dist;
     args.tile_halo = g_spmv_dist ? p->halo : nullptr;
     { static int dbg = -1; if (dbg < 0) { const char *e = getenv("SMLE_SPMV_DEBUG"); dbg = e ? atoi(e) : 0; } args.debug_flags = dbg; }
+    { static int med = -1; if (med < 0) { med = env_int("SMLE_SPMV_MEDLO", kRowPathMaxLen); if (med < 8) med = 8; if (med > kRowPathMaxLen) med = kRowPathMaxLen; } args.med_lo = med; }
     launch_kernel(kern, dim3(grid), dim3(THREADS + 32), smem, args, cg);   // + the producer warp
     ++g_launches;
     return check_launch("spmv_kernel");

@@ -110,6 +110,7 @@ struct SpmvArgs {
     V *dot_part;                       // [gridDim.x]  (DOT)
     unsigned int *ticket;
     int debug_flags;                   // 1: skip compute (stream-only ceiling of the TMA pipeline)
+    int med_lo;                        // general tiles: segments longer than this are queued for a warp (default kRowPathMaxLen)
     const DistCtl *dist;               // row-partitioned solve: halo waits, p.Ap posted to every peer (else NULL)
     const unsigned char *tile_halo;    // row-partitioned solve: 1 for tiles that gather halo columns (else NULL)
 };
@@ -131,8 +132,9 @@ struct SpmvSmem {
 constexpr int kRowPathMaxLen = 32;
 // longest row segment one warp reduces by itself; longer ones are strided over by the whole CTA
 constexpr int kWarpRowMax = 1024;
-// capacity of the per-tile queue of such segments (a tile of 3840 nonzeros holds at most 116 rows longer than 32)
-constexpr int kLongCap = 128;
+// capacity of the per-tile queue of such segments (a tile of 3840 nonzeros holds at most 116 rows longer than 32,
+// 480 longer than 7: the threshold can be lowered to 8 for experiments)
+constexpr int kLongCap = 512;
 
 // One warp per tile: the longest run of nonzeros of a single row inside the tile (complete rows,
 // the leading part of row x0 and the trailing part of row x1).  A property of the matrix and the
@@ -474,8 +476,8 @@ spmv_kernel(SpmvArgs<V> a, CgScalars cg)
                         }
                         const int len = end - beg;
                         V sum = 0;
-                        if (valid && len <= kRowPathMaxLen) sum = row_sum<V, COH>(a.x, pc, pv, beg, end);
-                        const bool is_med = valid && len > kRowPathMaxLen && len <= kWarpRowMax;
+                        if (valid && len <= a.med_lo) sum = row_sum<V, COH>(a.x, pc, pv, beg, end);
+                        const bool is_med = valid && len > a.med_lo && len <= kWarpRowMax;
                         if (balance && is_med) s_long[qc][atomicAdd(&s_nlong[qc], 1) & (kLongCap - 1)] = i;
                         unsigned med = __ballot_sync(0xffffffffu, is_med && !balance);
                         while (med) {
