@@ -137,6 +137,16 @@ int smle_cg_multi_f64(smle_csr_t a, const double *B, double *X, int k, int max_i
                       double *max_err_hist, int hist_capacity, int *hist_len,
                       double *final_rel_res);
 
+/* fp32 variants: CGSolveSingle / CGSolveMultiple as the reference's templates
+ * instantiate them for <float,int> (the reference drivers only use <double,int>).  The handle must be
+ * an fp32 one (smle_csr_create_f32); blocks are float, the scalars of the recurrence and all dot
+ * products are accumulated in double; histories and residuals are reported as double. */
+int smle_cg_single_f32(smle_csr_t a, const float *b, float *x, int max_iters, float tol,
+                       int is_device_ptr, int *iters_out, double *final_rel_res);
+int smle_cg_multi_f32(smle_csr_t a, const float *B, float *X, int k, int max_iters, float tol,
+                      int kernel, int is_device_ptr, int *iters_out, double *max_err_hist,
+                      int hist_capacity, int *hist_len, double *final_rel_res);
+
 /* ---- SPAI-preconditioned multi-RHS CG -------------------------------
  * smle_spai_build_f64 replaces SparseApproximateInversion
  *   (work_2025/cg/sparse_approximate_inversion.hpp:41-321): HOST code, like the reference -- the

@@ -132,6 +132,8 @@ struct CgWorkspace {
     cudaGraphExec_t graph = nullptr;                    // `graph_iters` iterations of K1,K2,K3
     int graph_iters = 0;
     unsigned graph_epoch = 0;                           // scratch_epoch of the handle when the graph was captured
+    cudaGraphExec_t graph32 = nullptr;                  // the same for the fp32 solver (blocks reinterpreted as float)
+    unsigned graph32_epoch = 0;
     // SPAI-preconditioned CG: z = M r, and the iteration graph (A step, x/r update, M step, p update)
     double *Z = nullptr;
     cudaGraphExec_t pcg_graph = nullptr;
@@ -161,7 +163,7 @@ struct smle_csr_s {
     int max_ctas = 0;
     int *carry_row = nullptr;
     void *carry_val = nullptr;  int carry_k = 0;
-    void *dot_part = nullptr, *fix_part = nullptr;
+    void *dot_part = nullptr, *fix_part = nullptr, *dot_sum = nullptr;
     unsigned int *ticket = nullptr;
     void *tile_carry = nullptr;       // carry slots of spmm_rows_kernel (sentinel-filled)
     size_t tile_carry_elems = 0;
@@ -181,6 +183,7 @@ void free_workspace(CgWorkspace &w)
 {
     if (w.graph) cudaGraphExecDestroy(w.graph);
     if (w.pcg_graph) cudaGraphExecDestroy(w.pcg_graph);
+    if (w.graph32) cudaGraphExecDestroy(w.graph32);
     cudaFree(w.Z);
     cudaFree(w.R); cudaFree(w.P); cudaFree(w.AP); cudaFree(w.Bd); cudaFree(w.Xd);
     cudaFree(w.Bd2[0]); cudaFree(w.Bd2[1]); cudaFree(w.Xs);
@@ -252,12 +255,13 @@ int ensure_scratch(smle_csr_t a, int k)
     if (k > a->carry_k) {
         if (g_stream) cudaStreamSynchronize(g_stream);   // nothing in flight may still use the old buffers
         ++a->scratch_epoch;
-        cudaFree(a->carry_val); cudaFree(a->dot_part); cudaFree(a->fix_part);
-        a->carry_val = a->dot_part = a->fix_part = nullptr;
+        cudaFree(a->carry_val); cudaFree(a->dot_part); cudaFree(a->fix_part); cudaFree(a->dot_sum);
+        a->carry_val = a->dot_part = a->fix_part = a->dot_sum = nullptr;
         size_t bytes = (size_t)a->max_ctas * (size_t)k * 8;
         CU(cudaMalloc(&a->carry_val, bytes));
         CU(cudaMalloc(&a->dot_part, bytes));
         CU(cudaMalloc(&a->fix_part, bytes));
+        CU(cudaMalloc(&a->dot_sum, (size_t)k * 8));
         a->carry_k = k;
     }
     return SMLE_OK;
@@ -319,6 +323,7 @@ int launch_merge_t(smle_csr_t a, const V *X, V *Y, int k, const CgScalars &cg, b
     args.carry_val = (V *)a->carry_val;
     args.dot_part = (V *)a->dot_part;
     args.fix_part = (V *)a->fix_part;
+    args.dot_sum = (V *)a->dot_sum;
     args.ticket = a->ticket;
     launch_kernel(merge_kernel<V, G, VEC, IPW, U, DOT>, dim3(grid, col_blocks), dim3(kThreads), 0, args, cg);
     ++g_launches;
@@ -521,6 +526,7 @@ int launch_spmm_rows_t(smle_csr_t a, const V *X, V *Y, int k, const CgScalars &c
     args.sched = sched; args.sched_off = sched_off;
     args.tile_carry = (V *)a->tile_carry;
     args.dot_part = (V *)a->dot_part;
+    args.dot_sum = (V *)a->dot_sum;
     args.ticket = a->ticket;
     args.band = 0;
     static int ypol = -1;
@@ -616,6 +622,7 @@ int launch_spmm_band(smle_csr_t a, const double *X, double *Y, int k, const CgSc
     args.sched = nullptr; args.sched_off = nullptr;
     args.tile_carry = (V *)a->tile_carry;
     args.dot_part = (V *)a->dot_part;
+    args.dot_sum = (V *)a->dot_sum;
     args.ticket = a->ticket;
     args.band = band;
     args.y_policy = 1;
@@ -912,6 +919,7 @@ int ensure_workspace(smle_csr_t a, int k, int hist_cap)
         w.hist_cap = hist_cap;
         if (w.graph) { cudaGraphExecDestroy(w.graph); w.graph = nullptr; }
         if (w.pcg_graph) { cudaGraphExecDestroy(w.pcg_graph); w.pcg_graph = nullptr; }
+        if (w.graph32) { cudaGraphExecDestroy(w.graph32); w.graph32 = nullptr; }
     }
     return SMLE_OK;
 }
@@ -935,14 +943,31 @@ CgScalars make_scalars(CgWorkspace &w, int k)
     return s;
 }
 
-template <int G, int VEC>
-int launch_vec_t(int which, const CgVecArgs &va, const CgScalars &cg, int max_iters, double tol, int grid, int seq_base)
+template <typename V, int G, int VEC>
+int launch_vec_t(int which, const CgVecArgsT<V> &va, const CgScalars &cg, int max_iters, double tol, int grid, int seq_base)
 {
-    if (which == 0) cg_init_kernel<G, VEC><<<grid, kThreads, 0, g_stream>>>(va, cg, max_iters, tol, seq_base);
-    else if (which == 1) launch_kernel(cg_update_r_kernel<G, VEC>, dim3(grid), dim3(kThreads), 0, va, cg);
-    else launch_kernel(cg_update_xp_kernel<G, VEC>, dim3(grid), dim3(kThreads), 0, va, cg);
+    if (which == 0) cg_init_kernel<V, G, VEC><<<grid, kThreads, 0, g_stream>>>(va, cg, max_iters, tol, seq_base);
+    else if (which == 1) launch_kernel(cg_update_r_kernel<V, G, VEC>, dim3(grid), dim3(kThreads), 0, va, cg);
+    else launch_kernel(cg_update_xp_kernel<V, G, VEC>, dim3(grid), dim3(kThreads), 0, va, cg);
     ++g_launches;
     return check_launch("cg vector kernel");
+}
+
+// fp32 blocks: the generic kernels only (the k = 1 specialisations and the multi-GPU / preconditioned loops are fp64)
+int launch_vec(int which, const CgVecArgsT<float> &va, const CgScalars &cg, int max_iters = 0, double tol = 0.0, int seq_base = 0)
+{
+    int G, VEC;
+    pick_shape<float>(va.k, &G, &VEC);
+    const int W = kThreads / G;
+    long long want = ((long long)va.n + W - 1) / W;
+    int grid = (int)(want < (long long)g_sms * 8 ? want : (long long)g_sms * 8);
+    if (grid < 1) grid = 1;
+#define SMLE_CASE(g, v) if (G == g && VEC == v) return launch_vec_t<float, g, v>(which, va, cg, max_iters, tol, grid, seq_base);
+    SMLE_CASE(1, 1) SMLE_CASE(2, 1) SMLE_CASE(4, 1) SMLE_CASE(8, 1) SMLE_CASE(16, 1) SMLE_CASE(32, 1)
+    SMLE_CASE(1, 2) SMLE_CASE(2, 2) SMLE_CASE(4, 2) SMLE_CASE(8, 2) SMLE_CASE(16, 2) SMLE_CASE(32, 2)
+    SMLE_CASE(1, 4) SMLE_CASE(2, 4) SMLE_CASE(4, 4) SMLE_CASE(8, 4) SMLE_CASE(16, 4) SMLE_CASE(32, 4)
+#undef SMLE_CASE
+    return fail(SMLE_ERR_ARG, "no vector kernel for k=%d", va.k);
 }
 
 int launch_vec(int which, const CgVecArgs &va, const CgScalars &cg, int max_iters = 0, double tol = 0.0, int seq_base = 0)
@@ -975,7 +1000,7 @@ int launch_vec(int which, const CgVecArgs &va, const CgScalars &cg, int max_iter
     long long want = ((long long)va.n + W - 1) / W;
     int grid = (int)(want < (long long)g_sms * 8 ? want : (long long)g_sms * 8);
     if (grid < 1) grid = 1;
-#define SMLE_CASE(g, v) if (G == g && VEC == v) return launch_vec_t<g, v>(which, va, cg, max_iters, tol, grid, seq_base);
+#define SMLE_CASE(g, v) if (G == g && VEC == v) return launch_vec_t<double, g, v>(which, va, cg, max_iters, tol, grid, seq_base);
     SMLE_CASE(1, 1) SMLE_CASE(2, 1) SMLE_CASE(4, 1) SMLE_CASE(8, 1) SMLE_CASE(16, 1) SMLE_CASE(32, 1)
     SMLE_CASE(1, 2) SMLE_CASE(2, 2) SMLE_CASE(4, 2) SMLE_CASE(8, 2) SMLE_CASE(16, 2) SMLE_CASE(32, 2)
 #undef SMLE_CASE
@@ -1128,6 +1153,98 @@ int cg_solve(smle_csr_t a, const double *B, double *X, int k, int max_iters, dou
     if (!w.Bd) CU(cudaMalloc(&w.Bd, sizeof(double) * (w.nk ? w.nk : 1)));
     CU(cudaMemcpyAsync(w.Bd, B, sizeof(double) * w.nk, cudaMemcpyHostToDevice, g_stream));
     return cg_solve_device(a, w.Bd, nullptr, X, k, max_iters, tol, iters_out, hist, hist_capacity, hist_len, final_rel);
+}
+
+// ---- fp32 CG: CGSolveSingle / CGSolveMultiple instantiated for <float,int> ----------
+// Same three kernels per iteration with float blocks (the workspace buffers are reused, reinterpreted);
+// scalars, dot partials and their reductions stay double.
+int cg32_solve_device(smle_csr_t a, const float *B, float *X_dev, float *X_host, int k, int max_iters, double tol,
+                      int *iters_out, double *hist_out, int hist_capacity, int *hist_len, double *final_rel)
+{
+    const bool want_hist = hist_out != nullptr && hist_capacity > 0;
+    int rc = ensure_workspace(a, k, want_hist ? (max_iters < hist_capacity ? max_iters : hist_capacity) : 0);
+    if (!rc) rc = ensure_scratch(a, k);
+    if (rc) return rc;
+    CgWorkspace &w = a->ws;
+    CgScalars cg = make_scalars(w, k);
+    CgVecArgsT<float> va;
+    va.B = B; va.X = (float *)w.Xd; va.R = (float *)w.R; va.P = (float *)w.P; va.AP = (float *)w.AP;
+    va.n = a->m; va.k = k; va.part = w.part; va.ticket = a->ticket + 1;
+    rc = launch_vec(0, va, cg, max_iters, tol);
+    if (rc) return rc;
+    auto iteration = [&]() -> int {
+        int r2 = launch_merge<float, true>(a, va.P, va.AP, k, cg);
+        if (!r2) r2 = launch_vec(1, va, cg);
+        if (!r2) r2 = launch_vec(2, va, cg);
+        return r2;
+    };
+    const bool use_graph = getenv("SMLE_NO_GRAPH") == nullptr;
+    if (w.graph32 && w.graph32_epoch != a->scratch_epoch) { cudaGraphExecDestroy(w.graph32); w.graph32 = nullptr; }
+    if (use_graph && !w.graph32) {
+        rc = launch_merge<float, true>(a, va.P, va.AP, k, cg, /*dry=*/true);
+        if (rc) return rc;
+        cudaGraph_t graph;
+        CU(cudaStreamBeginCapture(g_stream, cudaStreamCaptureModeThreadLocal));
+        for (int i = 0; i < kGraphIters && !rc; ++i) rc = iteration();
+        cudaError_t e = cudaStreamEndCapture(g_stream, &graph);
+        g_launches -= 3LL * kGraphIters;
+        if (rc) return rc;
+        if (e != cudaSuccess) return fail(SMLE_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(e));
+        e = cudaGraphInstantiate(&w.graph32, graph, 0);
+        cudaGraphDestroy(graph);
+        if (e != cudaSuccess) return fail(SMLE_ERR_CUDA, "graph instantiate failed: %s", cudaGetErrorString(e));
+        w.graph32_epoch = a->scratch_epoch;
+    }
+    const int batch = use_graph ? kGraphIters : 4;
+    rc = run_cg_batches(w, max_iters, batch, [&]() -> int {
+        if (use_graph) {
+            CU(cudaGraphLaunch(w.graph32, g_stream));
+            g_launches += 3LL * batch;
+            return SMLE_OK;
+        }
+        for (int i = 0; i < batch; ++i) {
+            int r2 = iteration();
+            if (r2) return r2;
+        }
+        return SMLE_OK;
+    });
+    if (rc) return rc;
+    const size_t xb = sizeof(float) * w.nk;
+    if (X_dev) CU(cudaMemcpyAsync(X_dev, w.Xd, xb, cudaMemcpyDeviceToDevice, g_stream));
+    if (X_host) CU(cudaMemcpyAsync(X_host, w.Xd, xb, cudaMemcpyDeviceToHost, g_stream));
+    CU(cudaMemcpyAsync(w.ctrl_host, w.ctrl, sizeof(int) * CTRL_WORDS, cudaMemcpyDeviceToHost, g_stream));
+    CU(cudaMemcpyAsync(w.ctrl_host + CTRL_WORDS, cg.last_rel, sizeof(double), cudaMemcpyDeviceToHost, g_stream));
+    CU(cudaStreamSynchronize(g_stream));
+    const int iters = w.ctrl_host[CTRL_ITER];
+    if (iters_out) *iters_out = iters;
+    if (final_rel) memcpy(final_rel, w.ctrl_host + CTRL_WORDS, sizeof(double));
+    if (want_hist) {
+        int nh = iters < w.hist_cap ? iters : w.hist_cap;
+        if (nh > hist_capacity) nh = hist_capacity;
+        CU(cudaMemcpyAsync(hist_out, w.hist, sizeof(double) * (size_t)nh, cudaMemcpyDeviceToHost, g_stream));
+        CU(cudaStreamSynchronize(g_stream));
+        if (hist_len) *hist_len = nh;
+    } else if (hist_len) {
+        *hist_len = 0;
+    }
+    return SMLE_OK;
+}
+
+int cg32_solve(smle_csr_t a, const float *B, float *X, int k, int max_iters, double tol, int is_device_ptr, int *iters_out,
+               double *hist, int hist_capacity, int *hist_len, double *final_rel)
+{
+    if (!a || !B || !X || k < 1) return fail(SMLE_ERR_ARG, "smle_cg (fp32): bad argument");
+    if (a->vbytes != 4) return fail(SMLE_ERR_ARG, "the fp32 solver needs an fp32 handle");
+    if (a->m != a->n) return fail(SMLE_ERR_ARG, "CG needs a square matrix");
+    int rc = ensure_init();
+    if (rc) return rc;
+    if (is_device_ptr) return cg32_solve_device(a, B, X, nullptr, k, max_iters, tol, iters_out, hist, hist_capacity, hist_len, final_rel);
+    rc = ensure_workspace(a, k, 0);
+    if (rc) return rc;
+    CgWorkspace &w = a->ws;
+    if (!w.Bd) CU(cudaMalloc(&w.Bd, sizeof(double) * (w.nk ? w.nk : 1)));
+    CU(cudaMemcpyAsync(w.Bd, B, sizeof(float) * w.nk, cudaMemcpyHostToDevice, g_stream));
+    return cg32_solve_device(a, (const float *)w.Bd, nullptr, X, k, max_iters, tol, iters_out, hist, hist_capacity, hist_len, final_rel);
 }
 
 // ---- SPAI-preconditioned multi-RHS CG ---------------------------------------------------------------
@@ -1428,7 +1545,7 @@ void smle_csr_destroy(smle_csr_t a)
         for (auto &sc : kv.second.scheds) { cudaFree(sc.second.sched); cudaFree(sc.second.off); }
     }
     cudaFree(a->ro); cudaFree(a->ci); cudaFree(a->va);
-    cudaFree(a->carry_row); cudaFree(a->carry_val); cudaFree(a->dot_part); cudaFree(a->fix_part);
+    cudaFree(a->carry_row); cudaFree(a->carry_val); cudaFree(a->dot_part); cudaFree(a->fix_part); cudaFree(a->dot_sum);
     cudaFree(a->ticket); cudaFree(a->tile_carry); cudaFree(a->cta_slot);
     delete a;
 }
@@ -1567,6 +1684,19 @@ int smle_pcg_spai_multi_f64(smle_csr_t a, smle_csr_t m, const double *B, double 
     if (!w.Bd) CU(cudaMalloc(&w.Bd, sizeof(double) * (w.nk ? w.nk : 1)));
     CU(cudaMemcpyAsync(w.Bd, B, sizeof(double) * w.nk, cudaMemcpyHostToDevice, g_stream));
     return pcg_solve_device(a, m, w.Bd, nullptr, X, k, max_iters, tol, iters_out, hist, hist_capacity, hist_len, final_rel_res);
+}
+
+int smle_cg_single_f32(smle_csr_t a, const float *b, float *x, int max_iters, float tol, int dev, int *iters_out,
+                       double *final_rel_res)
+{
+    return cg32_solve(a, b, x, 1, max_iters, (double)tol, dev, iters_out, nullptr, 0, nullptr, final_rel_res);
+}
+
+int smle_cg_multi_f32(smle_csr_t a, const float *B, float *X, int k, int max_iters, float tol, int kernel, int dev,
+                      int *iters_out, double *hist, int hist_capacity, int *hist_len, double *final_rel_res)
+{
+    if (kernel < SMLE_SIMPLE || kernel > SMLE_NONZERO_SPLIT) return fail(SMLE_ERR_ARG, "unknown SpmmKernel %d", kernel);
+    return cg32_solve(a, B, X, k, max_iters, (double)tol, dev, iters_out, hist, hist_capacity, hist_len, final_rel_res);
 }
 
 int smle_cg_run_fixed_f64(smle_csr_t a, const double *B, double *X, int k, int iters)

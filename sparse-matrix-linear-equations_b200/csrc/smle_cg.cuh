@@ -21,17 +21,21 @@
 
 namespace smle {
 
-struct CgVecArgs {
-    const double *__restrict__ B;
-    double *__restrict__ X;
-    double *__restrict__ R;
-    double *__restrict__ P;
-    double *__restrict__ AP;
+// V = value type of the blocks (double: the reference's solvers; float: the fp32 variant).  Scalars, dot
+// partials and their reductions are double for both.
+template <typename V>
+struct CgVecArgsT {
+    const V *__restrict__ B;
+    V *__restrict__ X;
+    V *__restrict__ R;
+    V *__restrict__ P;
+    V *__restrict__ AP;
     int n, k;
     double *part;          // [gridDim.x * k] per-CTA partials
     unsigned int *ticket;
-    double *__restrict__ Z = nullptr;   // preconditioned residual z = M r (SPAI-PCG only)
+    V *__restrict__ Z = nullptr;   // preconditioned residual z = M r (SPAI-PCG only)
 };
+using CgVecArgs = CgVecArgsT<double>;
 
 // reduce VEC per-lane partials over the workers of a CTA and publish them for this CTA
 template <int G, int VEC>
@@ -65,9 +69,9 @@ __device__ __forceinline__ void publish_partials(double (&s)[VEC], int cb, int k
 // single_strategy.hpp:120-131).  Last CTA: bnorm = sqrt(b.b) (0 -> 1), rs_old = b.b,
 // latches cleared, control words reset.
 // ---------------------------------------------------------------------------------------
-template <int G, int VEC>
+template <typename V, int G, int VEC>
 __global__ void __launch_bounds__(kThreads)
-cg_init_kernel(CgVecArgs a, CgScalars cg, int max_iters, double tol, int seq_base)
+cg_init_kernel(CgVecArgsT<V> a, CgScalars cg, int max_iters, double tol, int seq_base)
 {
     constexpr int W = kThreads / G, KB = G * VEC;
     __shared__ double s_w[kWarps][KB];
@@ -83,13 +87,13 @@ cg_init_kernel(CgVecArgs a, CgScalars cg, int max_iters, double tol, int seq_bas
         if (c0 < a.k) {
             for (int row = blockIdx.x * W + w; row < a.n; row += gridDim.x * W) {
                 size_t off = (size_t)row * k + c0;
-                double b[VEC], z[VEC];
-                ldg_vec<double, VEC>(b, a.B + off);
+                V b[VEC], z[VEC];
+                ldg_vec<V, VEC>(b, a.B + off);
 #pragma unroll
-                for (int v = 0; v < VEC; ++v) { z[v] = 0; s[v] += b[v] * b[v]; }
-                st_vec<double, VEC>(a.X + off, z);
-                st_vec<double, VEC>(a.R + off, b);
-                st_vec<double, VEC>(a.P + off, b);
+                for (int v = 0; v < VEC; ++v) { z[v] = 0; s[v] += (double)b[v] * (double)b[v]; }
+                st_vec<V, VEC>(a.X + off, z);
+                st_vec<V, VEC>(a.R + off, b);
+                st_vec<V, VEC>(a.P + off, b);
             }
         }
         publish_partials<G, VEC>(s, cb, a.k, a.part, s_w);
@@ -119,7 +123,8 @@ cg_init_kernel(CgVecArgs a, CgScalars cg, int max_iters, double tol, int seq_bas
 // relative residual and latch (no_pretreatment.hpp:133-155), beta (:165-176), rs_old <- rs_new
 // (:179-181), error history, iteration count, stop flag (:157-161 or max_iters).
 // ---------------------------------------------------------------------------------------
-__device__ __forceinline__ void cg_finalize_r(const CgVecArgs &a, const CgScalars &cg, double *s_red, int *s_cnt, bool pcg = false)
+template <typename Args>
+__device__ __forceinline__ void cg_finalize_r(const Args &a, const CgScalars &cg, double *s_red, int *s_cnt, bool pcg = false)
 {
     const int tid = threadIdx.x;
     if (a.k == 1) {
@@ -187,9 +192,9 @@ __device__ __forceinline__ void cg_finalize_r(const CgVecArgs &a, const CgScalar
 // Last CTA: rs_new, per-column relative residual and latch (:133-155), beta (:165-176),
 // rs_old <- rs_new (:179-181), history, iteration count, stop flag (:157-161 or max_iters).
 // ---------------------------------------------------------------------------------------
-template <int G, int VEC>
+template <typename V, int G, int VEC>
 __global__ void __launch_bounds__(kThreads)
-cg_update_r_kernel(CgVecArgs a, CgScalars cg)
+cg_update_r_kernel(CgVecArgsT<V> a, CgScalars cg)
 {
     constexpr int W = kThreads / G, KB = G * VEC;
     __shared__ double s_w[kWarps][KB];
@@ -207,17 +212,17 @@ cg_update_r_kernel(CgVecArgs a, CgScalars cg)
 #pragma unroll
         for (int v = 0; v < VEC; ++v) s[v] = 0;
         if (c0 < a.k) {
-            double na[VEC];
+            V na[VEC];
 #pragma unroll
-            for (int v = 0; v < VEC; ++v) na[v] = -cg.alpha[c0 + v];
+            for (int v = 0; v < VEC; ++v) na[v] = (V)(-cg.alpha[c0 + v]);
             for (int row = blockIdx.x * W + w; row < a.n; row += gridDim.x * W) {
                 size_t off = (size_t)row * k + c0;
-                double r[VEC], ap[VEC];
-                ld_vec<double, VEC>(r, a.R + off);
-                ld_vec<double, VEC>(ap, a.AP + off);
+                V r[VEC], ap[VEC];
+                ld_vec<V, VEC>(r, a.R + off);
+                ld_vec<V, VEC>(ap, a.AP + off);
 #pragma unroll
-                for (int v = 0; v < VEC; ++v) { r[v] += na[v] * ap[v]; s[v] += r[v] * r[v]; }
-                st_vec<double, VEC>(a.R + off, r);
+                for (int v = 0; v < VEC; ++v) { r[v] += na[v] * ap[v]; s[v] += (double)r[v] * (double)r[v]; }
+                st_vec<V, VEC>(a.R + off, r);
             }
         }
         publish_partials<G, VEC>(s, cb, a.k, a.part, s_w);
@@ -232,9 +237,9 @@ cg_update_r_kernel(CgVecArgs a, CgScalars cg)
 // P = R + beta * P (:177).  HALT is raised by the first K1 that sees STOP, i.e. after the
 // final iteration's K3 has run.
 // ---------------------------------------------------------------------------------------
-template <int G, int VEC>
+template <typename V, int G, int VEC>
 __global__ void __launch_bounds__(kThreads)
-cg_update_xp_kernel(CgVecArgs a, CgScalars cg)
+cg_update_xp_kernel(CgVecArgsT<V> a, CgScalars cg)
 {
     constexpr int W = kThreads / G, KB = G * VEC;
     griddep_wait();
@@ -247,23 +252,23 @@ cg_update_xp_kernel(CgVecArgs a, CgScalars cg)
     for (int cb = 0; cb * KB < a.k; ++cb) {
         const int c0 = cb * KB + li * VEC;
         if (c0 >= a.k) continue;
-        double al[VEC], be[VEC];
+        V al[VEC], be[VEC];
 #pragma unroll
-        for (int v = 0; v < VEC; ++v) { al[v] = cg.alpha[c0 + v]; be[v] = cg.beta[c0 + v]; }
+        for (int v = 0; v < VEC; ++v) { al[v] = (V)cg.alpha[c0 + v]; be[v] = (V)cg.beta[c0 + v]; }
         for (int row = blockIdx.x * W + w; row < a.n; row += gridDim.x * W) {
             size_t off = (size_t)row * k + c0;
-            double x[VEC], p[VEC];
-            ld_vec<double, VEC>(x, a.X + off);
-            ld_vec<double, VEC>(p, a.P + off);
+            V x[VEC], p[VEC];
+            ld_vec<V, VEC>(x, a.X + off);
+            ld_vec<V, VEC>(p, a.P + off);
 #pragma unroll
             for (int v = 0; v < VEC; ++v) x[v] += al[v] * p[v];
-            st_vec<double, VEC>(a.X + off, x);
+            st_vec<V, VEC>(a.X + off, x);
             if (!final_iter) {
-                double r[VEC];
-                ld_vec<double, VEC>(r, a.R + off);
+                V r[VEC];
+                ld_vec<V, VEC>(r, a.R + off);
 #pragma unroll
                 for (int v = 0; v < VEC; ++v) p[v] = r[v] + be[v] * p[v];
-                st_vec<double, VEC>(a.P + off, p);
+                st_vec<V, VEC>(a.P + off, p);
             }
         }
     }

@@ -45,6 +45,7 @@ struct MergeArgs {
     V *carry_val;                      // [gridDim.x*k] its partial sum
     V *dot_part;                       // [gridDim.x*k] per-CTA dot partials        (DOT)
     V *fix_part;                       // [gridDim.x*k] dot share of the carry fix  (DOT)
+    V *dot_sum;                        // [k] reduced dot products before they become the solver's scalars (DOT)
     unsigned int *ticket;
 };
 
@@ -335,9 +336,9 @@ merge_kernel(MergeArgs<V> a, CgScalars cg)
     if constexpr (DOT) {
         __syncthreads();
         // pAp[c] then alpha[c] = latched ? 0 : rs_old/pAp  (no_pretreatment.hpp:107-120)
-        cta_reduce_columns<V>(a.dot_part, a.fix_part, entries, a.k, (V *)cg.pAp, s_red);
+        cta_reduce_columns<V>(a.dot_part, a.fix_part, entries, a.k, a.dot_sum, s_red);   // (V-typed scratch: the scalars are double)
         for (int c = tid; c < a.k; c += kThreads)
-            cg_dot_scalars(cg, c, (double)cg.pAp[c]);
+            cg_dot_scalars(cg, c, (double)a.dot_sum[c]);
     }
 }
 

@@ -146,6 +146,7 @@ struct SpmmArgs {
     const int *sched_off;              //   sched[sched_off[b]] and end with the sentinel num_tiles; NULL -> the deal above
     V *tile_carry;                     // [num_tiles * k] carry slots, sentinel when empty
     V *dot_part;                       // [gridDim.x * k]  (DOT)
+    V *dot_sum;                        // [k] reduced dot products before they become the solver's scalars (DOT)
     unsigned int *ticket;
     int band;                          // RING > 0: half-width of the window around the tile's rows kept in the ring
     int y_policy;                      // 1: stream Y with L2 evict-first
@@ -559,9 +560,9 @@ spmm_rows_kernel(SpmmArgs<V> a, CgScalars cg)
             a.dot_part[(size_t)blockIdx.x * k + tid] = sdot;
         }
         if (!last_cta_election(a.ticket, gridDim.x)) return;
-        cta_reduce_columns<V>(a.dot_part, nullptr, gridDim.x, a.k, (V *)cg.pAp, s_red);
+        cta_reduce_columns<V>(a.dot_part, nullptr, gridDim.x, a.k, a.dot_sum, s_red);   // (V-typed scratch: the scalars are double)
         for (int c = tid; c < a.k; c += blockDim.x)
-            cg_dot_scalars(cg, c, (double)cg.pAp[c]);
+            cg_dot_scalars(cg, c, (double)a.dot_sum[c]);
     }
 }
 

@@ -137,10 +137,10 @@ inline void GpuCsrSpmmT(int t, CsrT &a, ValueT *x, ValueT *y, int k)
 template <typename ValueT, typename CsrT>
 inline int GpuCGSolveSingle(CsrT &a, const ValueT *b, ValueT *x, int max_iters, ValueT tolerance)
 {
-    static_assert(sizeof(ValueT) == 8, "the reference instantiates CG for <double,int> only");
-    int iters = 0;
-    if (smle_cg_single_f64(smle_adapters::handle_of(a), b, x, max_iters, tolerance, 0, &iters, nullptr))
-        smle_adapters::die("smle_cg_single_f64");
+    int iters = 0, rc;
+    if constexpr (sizeof(ValueT) == 8) rc = smle_cg_single_f64(smle_adapters::handle_of(a), b, x, max_iters, tolerance, 0, &iters, nullptr);
+    else rc = smle_cg_single_f32(smle_adapters::handle_of(a), b, x, max_iters, tolerance, 0, &iters, nullptr);
+    if (rc) smle_adapters::die("smle_cg_single");
     return iters;
 }
 
@@ -148,12 +148,15 @@ template <typename ValueT, typename CsrT>
 inline int GpuCGSolveMultiple(CsrT &a, const ValueT *B, ValueT *X, int num_vectors, int max_iters, ValueT tolerance,
                               int kernel_type, std::vector<double> *max_errors = nullptr)
 {
-    static_assert(sizeof(ValueT) == 8, "the reference instantiates CG for <double,int> only");
-    int iters = 0, hist_len = 0;
+    int iters = 0, hist_len = 0, rc;
     std::vector<double> hist(max_errors ? (size_t)(max_iters > 0 ? max_iters : 1) : 0);
-    if (smle_cg_multi_f64(smle_adapters::handle_of(a), B, X, num_vectors, max_iters, tolerance, kernel_type, 0, &iters,
-                          max_errors ? hist.data() : nullptr, (int)hist.size(), &hist_len, nullptr))
-        smle_adapters::die("smle_cg_multi_f64");
+    if constexpr (sizeof(ValueT) == 8)
+        rc = smle_cg_multi_f64(smle_adapters::handle_of(a), B, X, num_vectors, max_iters, tolerance, kernel_type, 0, &iters,
+                               max_errors ? hist.data() : nullptr, (int)hist.size(), &hist_len, nullptr);
+    else
+        rc = smle_cg_multi_f32(smle_adapters::handle_of(a), B, X, num_vectors, max_iters, tolerance, kernel_type, 0, &iters,
+                               max_errors ? hist.data() : nullptr, (int)hist.size(), &hist_len, nullptr);
+    if (rc) smle_adapters::die("smle_cg_multi");
     if (max_errors) max_errors->assign(hist.begin(), hist.begin() + hist_len);
     return iters;
 }

@@ -120,6 +120,8 @@ def _arg(x, dtype, writable=False):
             if cur.cuda_stream != get_stream():
                 cur.synchronize()
         return _P(x.data_ptr()), (1 if x.is_cuda else 0), x
+    if isinstance(x, np.ndarray) and x.dtype.kind == "f" and x.dtype != np.dtype(dtype):
+        raise SmleError(f"array of {x.dtype} passed where the handle computes in {np.dtype(dtype)}")
     a = np.ascontiguousarray(x, dtype=dtype)
     if writable and a is not x:
         raise SmleError("output array must be a contiguous numpy array of the value type")
@@ -226,14 +228,15 @@ class CsrMatrix:
     # -- CG -------------------------------------------------------------------------------------
     def cg_solve_single(self, b, max_iters: int, tolerance: float, out=None):
         """-> (iterations, x, final_rel_res)   CGSolveSingle (single_strategy.hpp:105-170)."""
-        pb, dev, kb = _arg(b, np.float64)
-        x = out if out is not None else _empty_like_arg(b, (self.num_rows,), np.float64)
-        px, dev_x, kx = _arg(x, np.float64, writable=True)
+        pb, dev, kb = _arg(b, self.dtype)
+        x = out if out is not None else _empty_like_arg(b, (self.num_rows,), self.dtype)
+        px, dev_x, kx = _arg(x, self.dtype, writable=True)
         if dev != dev_x:
             raise SmleError("b and x must both be host or both be device memory")
         it, rel = _I(0), _D(0)
-        _check(lib().smle_cg_single_f64(self._h, pb, px, _I(max_iters), _D(tolerance), _I(dev),
-                                        C.byref(it), C.byref(rel)))
+        tol = _D(tolerance) if self._s == "f64" else _F(tolerance)
+        _check(getattr(lib(), f"smle_cg_single_{self._s}")(self._h, pb, px, _I(max_iters), tol, _I(dev),
+                                                           C.byref(it), C.byref(rel)))
         return it.value, x, rel.value
 
     def cg_solve_single_batch(self, b_vectors, max_iters: int, tolerance: float, out=None):
@@ -256,18 +259,19 @@ class CsrMatrix:
         """-> (iterations, X, max_errors, final_rel_res)
         CGSolveMultiple (no_pretreatment.hpp:35-197); B, X row-major n x k."""
         k = int(B.shape[1])
-        pB, dev, kB = _arg(B, np.float64)
-        X = out if out is not None else _empty_like_arg(B, (self.num_rows, k), np.float64)
-        pX, dev_x, kX = _arg(X, np.float64, writable=True)
+        pB, dev, kB = _arg(B, self.dtype)
+        X = out if out is not None else _empty_like_arg(B, (self.num_rows, k), self.dtype)
+        pX, dev_x, kX = _arg(X, self.dtype, writable=True)
         if dev != dev_x:
             raise SmleError("B and X must both be host or both be device memory")
         cap = max(int(max_iters), 1) if want_history else 0
         hist = np.zeros(cap, dtype=np.float64) if want_history else None
         it, hl, rel = _I(0), _I(0), _D(0)
-        _check(lib().smle_cg_multi_f64(self._h, pB, pX, _I(k), _I(max_iters), _D(tolerance),
-                                       _I(kernel_type), _I(dev), C.byref(it),
-                                       hist.ctypes.data_as(_P) if want_history else None, _I(cap),
-                                       C.byref(hl), C.byref(rel)))
+        tol = _D(tolerance) if self._s == "f64" else _F(tolerance)
+        _check(getattr(lib(), f"smle_cg_multi_{self._s}")(self._h, pB, pX, _I(k), _I(max_iters), tol,
+                                                          _I(kernel_type), _I(dev), C.byref(it),
+                                                          hist.ctypes.data_as(_P) if want_history else None, _I(cap),
+                                                          C.byref(hl), C.byref(rel)))
         return it.value, X, (hist[: hl.value].copy() if want_history else None), rel.value
 
     def pcg_spai_solve_multiple(self, M: "CsrMatrix", B, max_iters: int, tolerance: float, kernel_type: int = MERGE,
