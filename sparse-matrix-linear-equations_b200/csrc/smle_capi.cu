@@ -147,6 +147,7 @@ struct Partition {
     int2 *xy = nullptr;   // device, num_tiles + 1
     int *maxlen = nullptr; // device, num_tiles: longest in-tile row segment
     int max_len = 0;       // max over maxlen[] (host copy): picks the SpMM kernel
+    int general_tiles = 0; // tiles whose longest segment exceeds kRowPathMaxLen (host copy): picks the SpMV configuration
     unsigned char *halo = nullptr;   // device, num_tiles: tile gathers halo columns (row-partitioned handles only)
     int band = -1;                   // window half-width of the band-window SpMM for this tiling (0: none, -1: unknown)
     // structure-aware SpMM tile schedules, keyed by grid size (smle_spmm.cuh); sched == nullptr: none
@@ -173,6 +174,7 @@ struct smle_csr_s {
     unsigned scratch_epoch = 0;
     int halo_base = -1;               // local block of a row partition: first halo column (else -1)
     int far_stride = -1;              // dominant far column offset in rows (0: none, -1: not probed yet)
+    int spmv_cfg = 0;                 // configuration of the single-vector kernel picked for this matrix (0: not yet)
     std::vector<int> common_offsets;  // column offsets > 0 that >= 40 % of the sampled rows have, descending
     CgWorkspace ws;
 };
@@ -218,13 +220,16 @@ int get_partition(smle_csr_t a, int items_per_tile, Partition **out)
     if (rc) return rc;
     {
         int *d_max = nullptr;
-        CU(cudaMalloc(&d_max, sizeof(int)));
-        CU(cudaMemsetAsync(d_max, 0, sizeof(int), g_stream));
-        int_max_kernel<<<(p.num_tiles + 255) / 256, 256, 0, g_stream>>>(p.maxlen, p.num_tiles, d_max);
+        int h_max[2] = {0, 0};
+        CU(cudaMalloc(&d_max, 2 * sizeof(int)));
+        CU(cudaMemsetAsync(d_max, 0, 2 * sizeof(int), g_stream));
+        int_max_kernel<<<(p.num_tiles + 255) / 256, 256, 0, g_stream>>>(p.maxlen, p.num_tiles, kRowPathMaxLen, d_max);
         ++g_launches;
-        CU(cudaMemcpyAsync(&p.max_len, d_max, sizeof(int), cudaMemcpyDeviceToHost, g_stream));
+        CU(cudaMemcpyAsync(h_max, d_max, 2 * sizeof(int), cudaMemcpyDeviceToHost, g_stream));
         CU(cudaStreamSynchronize(g_stream));
         cudaFree(d_max);
+        p.max_len = h_max[0];
+        p.general_tiles = h_max[1];
     }
     if (a->halo_base >= 0) {
         CU(cudaMalloc(&p.halo, (size_t)p.num_tiles));
@@ -724,12 +729,12 @@ int spmm_use_rows(smle_csr_t a, int G, int VEC, int k, bool dot, bool *use)
 //   STAGES  tiles in flight per CTA
 // The default was picked from the sweep in profiles/ (SMLE_SPMV_CFG=<threads>x<ipt>x<stages>
 // overrides it for experiments).
-template <typename V, int THREADS, int IPT, int STAGES, bool DOT>
+template <typename V, int THREADS, int IPT, int STAGES, bool DOT, int MAXB = 0>
 int launch_spmv_t(smle_csr_t a, const V *x, V *y, const CgScalars &cg, bool dry)
 {
     using SM = SpmvSmem<V, THREADS, IPT>;
     constexpr size_t smem = SM::STAGE_BYTES * STAGES;
-    auto kern = spmv_kernel<V, THREADS, IPT, STAGES, DOT>;
+    auto kern = spmv_kernel<V, THREADS, IPT, STAGES, DOT, MAXB>;
     Partition *p;
     int rc = get_partition(a, SM::TILE, &p);
     if (rc) return rc;
@@ -741,9 +746,16 @@ int launch_spmv_t(smle_csr_t a, const V *x, V *y, const CgScalars &cg, bool dry)
         CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, THREADS + 32, smem));
         if (occ < 1) return fail(SMLE_ERR_CUDA, "spmv_kernel does not fit on an SM (%zu B smem)", smem);
         if (occ > 8) occ = 8;
+        if (MAXB > 0 && occ > MAXB) occ = MAXB;
+        // (no carve-out preference: asking for the smallest carve-out that holds the resident CTAs -- more L1 --
+        // measured slower on R-MAT, 551 vs 533 us at scale 22; profiles/r02_spmv_skewed_cfg.txt)
     }
     if (dry) return SMLE_OK;
-    int max_ctas = g_sms * occ;
+    // SMLE_SPMV_WAVES=<w>: w times more CTAs than fit on the GPU at once, each with a shorter run of tiles; the
+    // hardware block scheduler then evens out runs of unequal cost (skewed matrices)
+    static int waves = 0;
+    if (!waves) { waves = env_int("SMLE_SPMV_WAVES", 1); if (waves < 1) waves = 1; }
+    int max_ctas = g_sms * occ * waves;
     if (max_ctas > a->max_ctas) max_ctas = a->max_ctas;
     int grid = p->num_tiles < max_ctas ? p->num_tiles : max_ctas;
     int tiles_per_cta = (p->num_tiles + grid - 1) / grid;
@@ -759,7 +771,17 @@ int launch_spmv_t(smle_csr_t a, const V *x, V *y, const CgScalars &cg, bool dry)
     args.dist = (const DistCtl *)g_spmv_dist;
     args.tile_halo = g_spmv_dist ? p->halo : nullptr;
     { static int dbg = -1; if (dbg < 0) { const char *e = getenv("SMLE_SPMV_DEBUG"); dbg = e ? atoi(e) : 0; } args.debug_flags = dbg; }
+    {
+        // small systems (matrix + the vectors of the caller: x, y, and r, p, x of a CG iteration) stay in the 126 MB L2
+        // from one product to the next when the matrix stream does not ask to be evicted first
+        static int keep_mb = -1;
+        if (keep_mb < 0) keep_mb = env_int("SMLE_SPMV_KEEP_MB", 96);
+        const size_t foot = (size_t)a->nnz * (4 + sizeof(V)) + ((size_t)a->m + 1) * 4 +
+                            (size_t)(DOT ? 5 : 2) * (size_t)(a->n > a->m ? a->n : a->m) * sizeof(V);
+        args.keep_l2 = foot <= (size_t)keep_mb * 1024 * 1024;
+    }
     { static int med = -1; if (med < 0) { med = env_int("SMLE_SPMV_MEDLO", kRowPathMaxLen); if (med < 8) med = 8; if (med > kRowPathMaxLen) med = kRowPathMaxLen; } args.med_lo = med; }
+    if (args.med_lo < SM::TILE / kLongCap + 1) args.med_lo = SM::TILE / kLongCap + 1;   // the tile's queue holds kLongCap segments
     launch_kernel(kern, dim3(grid), dim3(THREADS + 32), smem, args, cg);   // + the producer warp
     ++g_launches;
     return check_launch("spmv_kernel");
@@ -767,38 +789,78 @@ int launch_spmv_t(smle_csr_t a, const V *x, V *y, const CgScalars &cg, bool dry)
 
 constexpr int kSpmvThreads = 480, kSpmvIPT = 6, kSpmvStages = 2;   // default configuration (profiles/r01_spmv_sweeps.txt)
 
-int spmv_cfg()   // threads*10000 + ipt*100 + stages
+int spmv_cfg()   // threads*10000 + ipt*100 + stages (+ 10000000 * CTAs-per-SM cap, the optional 4th field)
 {
     static int cfg = -1;
     if (cfg < 0) {
         cfg = kSpmvThreads * 10000 + kSpmvIPT * 100 + kSpmvStages;
         const char *e = getenv("SMLE_SPMV_CFG");
-        int th = 0, i = 0, st = 0;
-        if (e && sscanf(e, "%dx%dx%d", &th, &i, &st) == 3) cfg = th * 10000 + i * 100 + st;
+        int th = 0, i = 0, st = 0, mb = 0;
+        if (e) {
+            const int nf = sscanf(e, "%dx%dx%dx%d", &th, &i, &st, &mb);
+            if (nf >= 3) cfg = th * 10000 + i * 100 + st + (nf == 4 ? mb : 0) * 10000000;
+        }
     }
     return cfg;
 }
 
 bool spmv_cfg_forced() { return getenv("SMLE_SPMV_CFG") != nullptr; }
 
-int spmv_tile_items(smle_csr_t a)
+constexpr int kSpmvCfgSmall = 480 * 10000 + 4 * 100 + 3;                 // 480x4x3
+constexpr int kSpmvCfgSkewed = 10000000 + 640 * 10000 + 6 * 100 + 2;     // 640x6x2, one CTA per SM
+
+// The configuration of the single-vector kernel for this matrix (cached on the handle):
+//   * SMLE_SPMV_CFG when set;
+//   * small problems (fewer than ~16 default tiles per CTA, e.g. grid2d 1000^2: 7): tiles of 1920 items in 3
+//     stages start the first row sooner and drain faster (profiles/r02_spmv_grid2d_1000_cfg_sweep.jsonl);
+//   * skewed matrices (a quarter of the default tiles or more hold a row segment longer than kRowPathMaxLen:
+//     R-MAT, the wheel): one CTA per SM with tiles of 3840 items -- the scattered x gathers of such matrices
+//     live on L1 capacity, and one CTA's stages leave L1 ~92 KB where two leave ~28 KB (R-MAT scale 23
+//     1.40 -> 1.04 ms, scale 24 3.91 -> 2.53 ms; profiles/r02_spmv_skewed_cfg.txt);
+//   * else 480x6x2.
+int spmv_pick(smle_csr_t a, int *cfg)
 {
-    if (!spmv_cfg_forced() && (long long)a->m + a->nnz < 16LL * kSpmvThreads * kSpmvIPT * 2 * g_sms) return 480 * 4;
-    return (spmv_cfg() / 10000) * ((spmv_cfg() / 100) % 100);
+    if (a->spmv_cfg) { *cfg = a->spmv_cfg; return SMLE_OK; }
+    int c = spmv_cfg();
+    if (!spmv_cfg_forced()) {
+        if ((long long)a->m + a->nnz < 16LL * kSpmvThreads * kSpmvIPT * 2 * g_sms) {
+            c = kSpmvCfgSmall;
+        } else {
+            Partition *p;
+            int rc = get_partition(a, kSpmvThreads * kSpmvIPT, &p);
+            if (rc) return rc;
+            static int skew_on = -1;
+            if (skew_on < 0) skew_on = env_int("SMLE_SPMV_SKEWED_CFG", 1);
+            if (skew_on && (long long)p->general_tiles * 4 >= p->num_tiles) c = kSpmvCfgSkewed;
+        }
+    }
+    a->spmv_cfg = *cfg = c;
+    return SMLE_OK;
+}
+
+int spmv_tile_items(smle_csr_t a, int *items)
+{
+    int c = 0;
+    int rc = spmv_pick(a, &c);
+    if (rc) return rc;
+    *items = ((c / 10000) % 1000) * ((c / 100) % 100);
+    return SMLE_OK;
 }
 
 template <typename V, bool DOT>
 int launch_spmv(smle_csr_t a, const V *x, V *y, const CgScalars &cg, bool dry)
 {
-    // small problems (fewer than ~16 default tiles per CTA, e.g. grid2d 1000^2: 7): tiles of 1920 items in 3
-    // stages start the first row sooner and drain faster (profiles/r02_spmv_grid2d_1000_cfg_sweep.jsonl)
-    if (!spmv_cfg_forced() && (long long)a->m + a->nnz < 16LL * kSpmvThreads * kSpmvIPT * 2 * g_sms)
-        return launch_spmv_t<V, 480, 4, 3, DOT>(a, x, y, cg, dry);
-    switch (spmv_cfg()) {
+    int c = 0;
+    int rc = spmv_pick(a, &c);
+    if (rc) return rc;
+    switch (c) {
 #define SMLE_CFG(th, i, st) case th * 10000 + i * 100 + st: return launch_spmv_t<V, th, i, st, DOT>(a, x, y, cg, dry);
         SMLE_CFG(480, 6, 2) SMLE_CFG(480, 5, 2) SMLE_CFG(480, 7, 2) SMLE_CFG(256, 12, 2) SMLE_CFG(224, 8, 2) SMLE_CFG(960, 4, 2)
         SMLE_CFG(480, 4, 3) SMLE_CFG(480, 3, 4) SMLE_CFG(320, 6, 3) SMLE_CFG(640, 6, 2)
 #undef SMLE_CFG
+#define SMLE_CFG1(th, i, st) case 10000000 + th * 10000 + i * 100 + st: return launch_spmv_t<V, th, i, st, DOT, 1>(a, x, y, cg, dry);
+        SMLE_CFG1(640, 6, 2) SMLE_CFG1(480, 6, 2) SMLE_CFG1(640, 9, 2) SMLE_CFG1(480, 8, 2) SMLE_CFG1(960, 6, 2) SMLE_CFG1(320, 12, 2)
+#undef SMLE_CFG1
     }
     return fail(SMLE_ERR_ARG, "unsupported SMLE_SPMV_CFG");
 }
@@ -1565,7 +1627,9 @@ int smle_csr_tile_coords(smle_csr_t a, int k, int *num_tiles, int *items_per_til
     if (!a || k < 1) return fail(SMLE_ERR_ARG, "bad argument");
     int rc = ensure_init();
     if (rc) return rc;
-    int items = spmv_tile_items(a);
+    int items = 0;
+    rc = spmv_tile_items(a, &items);
+    if (rc) return rc;
     if (k > 1) {   // the tiling of the SpMM kernel that would run for this (matrix, k)
         int G, VEC;
         if (a->vbytes == 8) pick_shape<double>(k, &G, &VEC); else pick_shape<float>(k, &G, &VEC);

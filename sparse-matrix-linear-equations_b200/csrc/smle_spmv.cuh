@@ -111,6 +111,8 @@ struct SpmvArgs {
     unsigned int *ticket;
     int debug_flags;                   // 1: skip compute (stream-only ceiling of the TMA pipeline)
     int med_lo;                        // general tiles: segments longer than this are queued for a warp (default kRowPathMaxLen)
+    int keep_l2;                       // 1: the whole system fits in L2 -- stream the matrix with the normal priority so that
+                                       //    the next product finds it there (else evict-first: read once per product)
     const DistCtl *dist;               // row-partitioned solve: halo waits, p.Ap posted to every peer (else NULL)
     const unsigned char *tile_halo;    // row-partitioned solve: 1 for tiles that gather halo columns (else NULL)
 };
@@ -135,6 +137,8 @@ constexpr int kWarpRowMax = 1024;
 // capacity of the per-tile queue of such segments (a tile of 3840 nonzeros holds at most 116 rows longer than 32,
 // 480 longer than 7: the threshold can be lowered to 8 for experiments)
 constexpr int kLongCap = 512;
+// segments longer than kWarpRowMax in one tile: at most TILE / (kWarpRowMax + 1) <= 7 for tiles of up to 8192 items
+constexpr int kHugeCap = 8;
 
 // One warp per tile: the longest run of nonzeros of a single row inside the tile (complete rows,
 // the leading part of row x0 and the trailing part of row x1).  A property of the matrix and the
@@ -170,12 +174,17 @@ __global__ void tile_halo_kernel(const int *__restrict__ ci, const int2 *__restr
     if (lane == 0) out[t] = any ? 1 : 0;
 }
 
-__global__ void int_max_kernel(const int *__restrict__ v, int n, int *out)
+// out[0] = max over v, out[1] = number of entries above `thresh` (the general tiles of a partition)
+__global__ void int_max_kernel(const int *__restrict__ v, int n, int thresh, int *out)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    int mx = i < n ? v[i] : 0;
-    mx = __reduce_max_sync(0xffffffffu, mx);
-    if ((threadIdx.x & 31) == 0 && mx > 0) atomicMax(out, mx);
+    const int val = i < n ? v[i] : 0;
+    const int mx = __reduce_max_sync(0xffffffffu, val);
+    const unsigned above = __ballot_sync(0xffffffffu, val > thresh);
+    if ((threadIdx.x & 31) == 0) {
+        if (mx > 0) atomicMax(out, mx);
+        if (above) atomicAdd(out + 1, __popc(above));
+    }
 }
 
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar)
@@ -253,6 +262,80 @@ __device__ __forceinline__ V strided_sum(const V *__restrict__ x, const int *pc,
     return sum;
 }
 
+// ---- general tiles, product-staged path ---------------------------------------------------------
+// The gather of x with an L2 cache hint in a register: evict-last when x is too large for the matrix
+// stream and the y stores to leave it alone (R-MAT scale 24: x = 134 MB against 126 MB of L2),
+// evict-normal otherwise.  Halo tiles (COH) keep the L2-coherent load.
+template <typename V, bool COH>
+__device__ __forceinline__ V gather_hint(const V *x, uint64_t pol)
+{
+    if constexpr (COH) {
+        return __ldcg(x);
+    } else if constexpr (sizeof(V) == 8) {
+        double v;
+        asm("ld.global.nc.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(x), "l"(pol));
+        return (V)v;
+    } else {
+        float v;
+        asm("ld.global.nc.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(v) : "l"(x), "l"(pol));
+        return (V)v;
+    }
+}
+
+template <typename V>
+__device__ __forceinline__ void store_hint(V *p, V v, uint64_t pol)
+{
+    if constexpr (sizeof(V) == 8)
+        asm volatile("st.global.L2::cache_hint.f64 [%0], %1, %2;" ::"l"(p), "d"((double)v), "l"(pol) : "memory");
+    else
+        asm volatile("st.global.L2::cache_hint.f32 [%0], %1, %2;" ::"l"(p), "f"((float)v), "l"(pol) : "memory");
+}
+
+__device__ __forceinline__ uint64_t l2_policy_evict_normal()
+{
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+
+// Sum of the staged products of one row segment, in nonzero order (the order of the per-row gather
+// path, so both paths round alike).  Four loads are requested before the first add.
+template <typename V>
+__device__ __forceinline__ V seg_sum(const V *pv, int beg, int end)
+{
+    V sum = 0;
+    for (; beg + 4 <= end; beg += 4) {
+        const V p0 = pv[beg], p1 = pv[beg + 1], p2 = pv[beg + 2], p3 = pv[beg + 3];
+        sum += p0; sum += p1; sum += p2; sum += p3;
+    }
+    for (; beg < end; ++beg) sum += pv[beg];
+    return sum;
+}
+
+// The same over the positions beg + id, beg + id + STRIDE, ... (lanes of a warp / threads of the CTA); four
+// independent partial sums, so a pass is bound by the shared-memory pipe and not by the add latency.
+template <typename V, int STRIDE>
+__device__ __forceinline__ V seg_sum_strided(const V *pv, int beg, int end, int id)
+{
+    V s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+    int z = beg + id;
+    for (; z + 3 * STRIDE < end; z += 4 * STRIDE) {
+        s0 += pv[z]; s1 += pv[z + STRIDE]; s2 += pv[z + 2 * STRIDE]; s3 += pv[z + 3 * STRIDE];
+    }
+    for (; z < end; z += STRIDE) s0 += pv[z];
+    return (s0 + s1) + (s2 + s3);
+}
+
+// Sum of n <= 32 per-warp parts by one warp (fixed tree: the result does not depend on timing)
+template <typename V>
+__device__ __forceinline__ V warp_sum_parts(const V *parts, int n, int lane)
+{
+    V v = lane < n ? parts[lane] : V(0);
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+    return v;
+}
+
 // Publisher side of the CTA-boundary exchange.  val = sum of the parts of row R = (row in progress
 // at the end of CTA c) that lie in CTAs <= c.  If the owner's part is already in slot c, finish the
 // row (owner part + carry); if CTA c+1 lies entirely inside the row, add its part and move on.
@@ -296,18 +379,25 @@ __device__ __noinline__ void cta_carry_publish(const int2 *__restrict__ tile_xy,
 // ---------------------------------------------------------------------------------------
 constexpr int kChainTiles = 512;   // tiles between two carry-chain resolutions of a CTA
 
-template <typename V, int THREADS, int IPT, int STAGES, bool DOT>
-__global__ void __launch_bounds__(THREADS + 32, spmv_ctas_per_sm<V, THREADS, IPT, STAGES>())
+//   MAXB > 0 caps the CTAs per SM below what shared memory allows: skewed matrices run ONE CTA per SM, so that the
+//   carve-out leaves 90-150 KB of L1 to the scattered x gathers instead of ~28 KB (R-MAT scale 24: 3.9 -> 2.5 ms)
+template <typename V, int THREADS, int IPT, int STAGES, bool DOT, int MAXB = 0>
+__global__ void __launch_bounds__(THREADS + 32, (MAXB > 0 && MAXB < spmv_ctas_per_sm<V, THREADS, IPT, STAGES>())
+                                                    ? MAXB : spmv_ctas_per_sm<V, THREADS, IPT, STAGES>())
 spmv_kernel(SpmvArgs<V> a, CgScalars cg)
 {
     using SM = SpmvSmem<V, THREADS, IPT>;
     constexpr int NW = THREADS / 32;
     constexpr int EPV = SM::EPV;
+    static_assert(SM::TILE / (kWarpRowMax + 1) < kHugeCap && NW >= kHugeCap - 1, "huge-segment bookkeeping of the general tiles");
 
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ uint64_t s_full[STAGES], s_empty[STAGES];
     __shared__ V s_wsum[NW];
-    __shared__ int s_huge[4], s_nhuge;       // row segments longer than kWarpRowMax in the current tile
+    __shared__ V s_hub[2][kHugeCap][NW];            // per-warp parts of the (at most kHugeCap) huge segments of a general tile, or of a tile
+                                             // that lies inside one row ([.][0]); double-buffered by general-tile parity
+    __shared__ int s_hq[3][kHugeCap], s_nhq[3];     // the huge segments of a tile (product-staged path; triple-buffered like s_long)
+    __shared__ int s_huge[kHugeCap], s_nhuge;       // row segments longer than kWarpRowMax in the current tile
     __shared__ int s_long[3][kLongCap], s_nlong[3], s_next[3];   // queued segments of 33..kWarpRowMax (balance mode)
     __shared__ V s_tcarry[kChainTiles];      // carry-out of each tile of the current chunk
     __shared__ int s_trow[kChainTiles];      // first row of the tile, or -1 when no row completes in it
@@ -344,7 +434,7 @@ spmv_kernel(SpmvArgs<V> a, CgScalars cg)
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         s_running = 0;
         s_nhuge = 0;
-        for (int q = 0; q < 3; ++q) { s_nlong[q] = 0; s_next[q] = 0; }
+        for (int q = 0; q < 3; ++q) { s_nlong[q] = 0; s_next[q] = 0; s_nhq[q] = 0; }
     }
     __syncthreads();
 
@@ -353,7 +443,8 @@ spmv_kernel(SpmvArgs<V> a, CgScalars cg)
     if (warp == NW) {
         // =============================== producer warp ===========================================
         if (lane == 0) {
-            const uint64_t pol_stream = l2_policy_evict_first();   // the matrix is read once per SpMV
+            // the matrix is read once per SpMV: evict-first, unless matrix and vectors together stay in L2
+            const uint64_t pol_stream = a.keep_l2 ? l2_policy_evict_normal() : l2_policy_evict_first();
             int2 lo = (t0 < t1) ? a.tile_xy[t0] : make_int2(0, 0);
             for (int t = t0; t < t1; ++t) {
                 const int it = t - t0, s = it % STAGES;
@@ -387,6 +478,9 @@ spmv_kernel(SpmvArgs<V> a, CgScalars cg)
         // kernel until it has completed.
         if constexpr (DOT) { griddep_wait(); griddep_launch_dependents(); }
         bool halo_ready = false;
+        // general tiles: L2 priorities of the x gathers and the y stores (debug_flags bit 3: x evict-last, y evict-first)
+        const uint64_t pol_x = (a.debug_flags & 8) ? l2_policy_evict_last() : l2_policy_evict_normal();
+        const uint64_t pol_y = (a.debug_flags & 8) ? l2_policy_evict_first() : l2_policy_evict_normal();
         int gen_count = 0;   // general tiles processed by this CTA so far (same in every thread)
         for (int t = t0; t < t1; ++t) {
             const int it = t - t0, s = it % STAGES, slot = it % kChainTiles;
@@ -438,8 +532,102 @@ spmv_kernel(SpmvArgs<V> a, CgScalars cg)
                 }
                 };
                 if (tile_halo) row_path(std::true_type{}); else row_path(std::false_type{});
+            } else if ((a.debug_flags & 4) == 0) {
+                // ---- general tile, product-staged: one gather per THREAD-item, then reductions from shared memory
+                // A power-law tile holds few rows (R-MAT x16: ~170 of 2880 items), so a thread per row leaves
+                // two thirds of the CTA without a gather to issue and walks its row in dependent rounds of global
+                // latency.  Here every thread requests the x of IPT nonzeros at once (coalesced over the staged
+                // indices), the products replace the staged values, and after ONE barrier the rows are summed from
+                // shared memory: <= med_lo by a thread, <= kWarpRowMax by a warp taking rows from the tile's queue,
+                // longer segments by the whole CTA.  A tile that lies inside one row (a hub row spans many tiles)
+                // never writes its products back: thread sums -> warp sums -> thread 0.
+                const int qc = gen_count % 3, qn = (gen_count + 1) % 3, hp = gen_count & 1;
+                ++gen_count;
+                if (tid == 0) { s_nlong[qn] = 0; s_next[qn] = 0; s_nhq[qn] = 0; }
+                auto emit = [&](int i, V sum) {
+                    if (i < rows) {
+                        store_hint<V>(a.y + x0 + i, sum, pol_y);
+                        if constexpr (DOT) dot += sum * __ldg(a.x + x0 + i);
+                    } else {
+                        s_tcarry[slot] = sum;
+                    }
+                };
+                auto staged = [&](auto coh) {
+                    constexpr bool COH = decltype(coh)::value;
+                    V xa[IPT];
+#pragma unroll
+                    for (int j = 0; j < IPT; ++j) xa[j] = gather_hint<V, COH>(a.x + pc[min(tid + j * THREADS, nz - 1)], pol_x);
+                    if (rows == 0) {
+                        V part = 0;
+#pragma unroll
+                        for (int j = 0; j < IPT; ++j)
+                            if (tid + j * THREADS < nz) part += pv[tid + j * THREADS] * xa[j];
+#pragma unroll
+                        for (int d = 16; d > 0; d >>= 1) part += __shfl_xor_sync(0xffffffffu, part, d);
+                        if (lane == 0) s_hub[hp][0][warp] = part;
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < IPT; ++j)
+                            if (tid + j * THREADS < nz) pv[tid + j * THREADS] *= xa[j];
+                        // queue the long segments while the gathers are in flight
+                        for (int i = tid; i <= rows; i += THREADS) {
+                            const int beg = (i == 0) ? 0 : s_re[i - 1] - y0;
+                            const int end = (i == rows) ? nz : s_re[i] - y0;
+                            const int len = end - beg;
+                            if (len > kWarpRowMax) s_hq[qc][atomicAdd(&s_nhq[qc], 1) & (kHugeCap - 1)] = i;
+                            else if (len > a.med_lo) s_long[qc][atomicAdd(&s_nlong[qc], 1) & (kLongCap - 1)] = i;
+                        }
+                    }
+                };
+                if (tile_halo) staged(std::true_type{}); else staged(std::false_type{});
+                consumer_sync<THREADS>();   // products and queues complete
+                if (rows == 0) {
+                    if (warp == 0) {
+                        const V total = warp_sum_parts<V>(s_hub[hp][0], NW, lane);
+                        if (lane == 0) s_tcarry[slot] = total;
+                    }
+                } else {
+                    // huge segments first: their per-warp parts must be complete at the tile's second barrier
+                    const bool has_huge = tile_ml > kWarpRowMax;   // uniform over the CTA
+                    const int nh = has_huge ? min(s_nhq[qc], kHugeCap) : 0;
+                    for (int h = 0; h < nh; ++h) {
+                        const int i = s_hq[qc][h];
+                        const int beg = (i == 0) ? 0 : s_re[i - 1] - y0;
+                        const int end = (i == rows) ? nz : s_re[i] - y0;
+                        V part = seg_sum_strided<V, THREADS>(pv, beg, end, tid);
+#pragma unroll
+                        for (int d = 16; d > 0; d >>= 1) part += __shfl_xor_sync(0xffffffffu, part, d);
+                        if (lane == 0) s_hub[hp][h][warp] = part;
+                    }
+                    for (int i = tid; i <= rows; i += THREADS) {
+                        const int beg = (i == 0) ? 0 : s_re[i - 1] - y0;
+                        const int end = (i == rows) ? nz : s_re[i] - y0;
+                        if (end - beg <= a.med_lo) emit(i, seg_sum<V>(pv, beg, end));
+                    }
+                    const int nl = min(s_nlong[qc], kLongCap);
+                    for (;;) {
+                        int idx = 0;
+                        if (lane == 0) idx = atomicAdd(&s_next[qc], 1);
+                        idx = __shfl_sync(0xffffffffu, idx, 0);
+                        if (idx >= nl) break;
+                        const int i = s_long[qc][idx];
+                        const int beg = (i == 0) ? 0 : s_re[i - 1] - y0;
+                        const int end = (i == rows) ? nz : s_re[i] - y0;
+                        V part = seg_sum_strided<V, 32>(pv, beg, end, lane);
+#pragma unroll
+                        for (int d = 16; d > 0; d >>= 1) part += __shfl_xor_sync(0xffffffffu, part, d);
+                        if (lane == 0) emit(i, part);
+                    }
+                    if (has_huge) {
+                        consumer_sync<THREADS>();   // per-warp parts of the huge segments complete
+                        if (warp < nh) {
+                            const V total = warp_sum_parts<V>(s_hub[hp][warp], NW, lane);
+                            if (lane == 0) emit(s_hq[qc][warp], total);
+                        }
+                    }
+                }
             } else {
-                // ---- general tile: rows of any length, three tiers, no merge walk -----------------------
+                // ---- general tile, per-row gathers (SMLE_SPMV_DEBUG=4; the default before the product-staged path)
                 //   <= kRowPathMaxLen  one thread per row segment (as above)
                 //   <= kWarpRowMax     the warp that found it reduces it: lanes stride over its nonzeros,
                 //                      shuffle tree; warp-private, no CTA barrier
@@ -489,7 +677,7 @@ spmv_kernel(SpmvArgs<V> a, CgScalars cg)
                             for (int d = 16; d > 0; d >>= 1) part += __shfl_xor_sync(0xffffffffu, part, d);
                             if (lane == src) sum = part;
                         }
-                        if (valid && len > kWarpRowMax) s_huge[atomicAdd(&s_nhuge, 1) & 3] = i;
+                        if (valid && len > kWarpRowMax) s_huge[atomicAdd(&s_nhuge, 1) & (kHugeCap - 1)] = i;
                         else if (valid && !(balance && is_med)) emit(i, sum);
                     }
                     if (balance || tile_ml > kWarpRowMax) consumer_sync<THREADS>();   // queues complete (uniform over the CTA)
@@ -510,7 +698,7 @@ spmv_kernel(SpmvArgs<V> a, CgScalars cg)
                         }
                     }
                     if (tile_ml > kWarpRowMax) {   // the tile's longest segment is known: uniform over the CTA
-                        const int nh = min(s_nhuge, 4);
+                        const int nh = min(s_nhuge, kHugeCap);
                         for (int h = 0; h < nh; ++h) {
                             const int i = s_huge[h];
                             const int beg = (i == 0) ? 0 : s_re[i - 1] - y0;

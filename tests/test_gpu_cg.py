@@ -59,6 +59,45 @@ def test_single_rhs_against_oracle_2d(gpu, orc):
     a.close()
 
 
+def _arrow_spd(n, fan, dtype=np.float64):
+    """SPD matrix with skewed rows: row 0 is a hub coupled to every vertex (spans several tiles), every
+    `fan`-th row is a medium hub coupled to the `fan` rows behind it, plus a tridiagonal part; strictly
+    diagonally dominant.  Exercises the general tiles of the single-vector kernel inside CG (fused p.Ap)."""
+    rows, cols, vals = [], [], []
+
+    def add(i, j, v):
+        rows.extend([i, j]); cols.extend([j, i]); vals.extend([v, v])
+
+    for j in range(1, n):
+        add(0, j, -1.0 / n)
+    for i in range(1, n - 1):
+        add(i, i + 1, -0.5)
+    for h in range(fan, n - fan, fan):
+        for j in range(h + 2, h + fan):
+            add(h, j, -0.25 / fan)
+    import scipy.sparse as sp
+    a = sp.coo_matrix((vals, (rows, cols)), shape=(n, n)).tocsr()
+    a = a + sp.diags(np.asarray(abs(a).sum(axis=1)).ravel() + 1.0)
+    a = a.tocsr(); a.sort_indices()
+    return a.indptr.astype(np.int32), a.indices.astype(np.int32), a.data.astype(dtype)
+
+
+def test_single_rhs_cg_on_skewed_spd_matrix(gpu, orc):
+    ro, ci, va = _arrow_spd(20000, 200)
+    n = len(ro) - 1
+    a = gpu.CsrMatrix(ro, ci, va)
+    b = gpu.gen_rhs_rand(5, n)
+    # the product alone first: hub row, medium rows and short rows against the gold loop
+    y = a.spmv(b)
+    y_o = orc.spmv_gold(ro, ci, va, b)
+    np.testing.assert_allclose(y, y_o, rtol=1e-12, atol=1e-13)
+    it, x, rel = a.cg_solve_single(b, 10000, 1e-10)
+    it_o, x_o = orc.cg_single(ro, ci, va, b, 10000, 1e-10)
+    assert _close_iters(it, it_o), (it, it_o)
+    np.testing.assert_allclose(x, x_o, rtol=1e-7, atol=1e-10)
+    a.close()
+
+
 def test_max_iters_cap_and_zero_iters(gpu):
     ro, ci, va = gpu.gen_grid3d(10, True, 6.0, -1.0)
     n = len(ro) - 1

@@ -17,7 +17,7 @@ LIB = ROOT / "sparse-matrix-linear-equations_b200" / "libsmle_b200.so"
 LOG = ROOT / "sparse-matrix-linear-equations_b200" / "build.log"
 
 # mangled-name fragments of the default configurations (smle_capi.cu: kSpmv*, kSpmm*)
-SPMV_DOT = "spmv_kernelIdLi480ELi6ELi2ELb1"
+SPMV_DOT = "spmv_kernelIdLi480ELi6ELi2ELb1ELi0E"
 SPMM = "spmm_rows_kernelIdLi16ELi2ELi1ELi4ELi960ELi1920ELi2ELi1ELb0"
 SPMM_DOT = "spmm_rows_kernelIdLi16ELi2ELi1ELi4ELi960ELi1920ELi2ELi1ELb1"
 
