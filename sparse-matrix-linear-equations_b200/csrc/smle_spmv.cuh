@@ -341,17 +341,20 @@ __device__ __forceinline__ V warp_sum_parts(const V *parts, int n, int lane)
 // row (owner part + carry); if CTA c+1 lies entirely inside the row, add its part and move on.
 template <typename V>
 __device__ __noinline__ void cta_carry_publish(const int2 *__restrict__ tile_xy, int tiles_per_cta, int num_tiles, int m,
-                                               V *cta_slot, V *y, int c, V val)
+                                               V *cta_slot, V *y, int c, V val, int row_first, int next_first)
 {
-    for (;;) {
-        const int row = tile_xy[min((c + 1) * tiles_per_cta, num_tiles)].x;
+    // row_first / next_first: the rows in progress at the end of CTA c and of CTA c+1, read by the caller at
+    // kernel start (the epilogue of a 20 us launch should not wait for two more dependent L2 round trips)
+    for (bool first = true;; first = false) {
+        const int row = first ? row_first : tile_xy[min((c + 1) * tiles_per_cta, num_tiles)].x;
         if (row >= m) return;
         V *slot = cta_slot + c;
         const V owner = slot_exchange<V>(slot, val);
         if (is_sentinel<V>(owner)) return;                 // the other party comes later and finishes
         slot_reset<V>(slot);
         __threadfence();                                   // its earlier stores to y[row] come before ours
-        if (tile_xy[min((c + 2) * tiles_per_cta, num_tiles)].x > row) {   // the row ends in CTA c+1
+        const int next = first ? next_first : tile_xy[min((c + 2) * tiles_per_cta, num_tiles)].x;
+        if (next > row) {                                  // the row ends in CTA c+1
             y[row] = owner + val;
             return;
         }
@@ -402,6 +405,7 @@ spmv_kernel(SpmvArgs<V> a, CgScalars cg)
     __shared__ V s_tcarry[kChainTiles];      // carry-out of each tile of the current chunk
     __shared__ int s_trow[kChainTiles];      // first row of the tile, or -1 when no row completes in it
     __shared__ V s_running;                  // carry chained so far (row in progress at the chunk start)
+    __shared__ int s_edge[3];                // rows in progress at the start / end of this CTA and at the end of the next one
     __shared__ V s_red[THREADS + 32];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -442,13 +446,25 @@ spmv_kernel(SpmvArgs<V> a, CgScalars cg)
 
     if (warp == NW) {
         // =============================== producer warp ===========================================
-        if (lane == 0) {
-            // the matrix is read once per SpMV: evict-first, unless matrix and vectors together stay in L2
-            const uint64_t pol_stream = a.keep_l2 ? l2_policy_evict_normal() : l2_policy_evict_first();
-            int2 lo = (t0 < t1) ? a.tile_xy[t0] : make_int2(0, 0);
-            for (int t = t0; t < t1; ++t) {
-                const int it = t - t0, s = it % STAGES;
-                const int2 hi = a.tile_xy[t + 1];
+        // All 32 lanes fetch the metadata of the next 32 tiles with one coalesced request per array (a
+        // dependent L2 round trip per tile in the single issuing lane delayed every stage of a short launch:
+        // grid2d 1000^2 has 11 tiles per CTA); lane 0 waits for the stage and issues the bulk copies.
+        // the matrix is read once per SpMV: evict-first, unless matrix and vectors together stay in L2
+        const uint64_t pol_stream = a.keep_l2 ? l2_policy_evict_normal() : l2_policy_evict_first();
+        int2 lo = a.tile_xy[min(t0, a.num_tiles)];
+        int2 hi_l = make_int2(0, 0);
+        int ml_l = 0, halo_l = 0;
+        for (int t = t0; t < t1; ++t) {
+            const int it = t - t0, s = it % STAGES, q = it & 31;
+            if (q == 0) {
+                const int tt = min(t + lane, a.num_tiles - 1);
+                hi_l = a.tile_xy[tt + 1];
+                ml_l = a.tile_maxlen[tt];
+                halo_l = a.tile_halo ? (int)a.tile_halo[tt] : 0;
+            }
+            const int2 hi = make_int2(__shfl_sync(0xffffffffu, hi_l.x, q), __shfl_sync(0xffffffffu, hi_l.y, q));
+            const int tile_ml_p = __shfl_sync(0xffffffffu, ml_l, q), tile_halo_p = __shfl_sync(0xffffffffu, halo_l, q);
+            if (lane == 0) {
                 if (it >= STAGES) {
                     mbar_wait(&s_empty[s], (uint32_t)(it / STAGES - 1) & 1u);
                     fence_proxy_async();
@@ -457,8 +473,8 @@ spmv_kernel(SpmvArgs<V> a, CgScalars cg)
                 // the consumers read them from shared memory after the wait on "full"
                 int *hdr = stage_hdr(s);
                 hdr[0] = lo.x; hdr[1] = lo.y; hdr[2] = hi.x; hdr[3] = hi.y;
-                hdr[4] = a.tile_maxlen[t];
-                hdr[5] = a.tile_halo ? (int)a.tile_halo[t] : 0;
+                hdr[4] = tile_ml_p;
+                hdr[5] = tile_halo_p;
                 const int yc = lo.y & ~3;                                   // 16 B aligned column start
                 const int yv = lo.y & ~(EPV - 1);                           // 16 B aligned value start
                 const int rb = (lo.x + 1) & ~3;                             // 16 B aligned row-offset start
@@ -469,14 +485,19 @@ spmv_kernel(SpmvArgs<V> a, CgScalars cg)
                 if (nb_col) tma_load_1d(stage_col(s), a.ci + yc, nb_col, &s_full[s], pol_stream);
                 if (nb_val) tma_load_1d(stage_val(s), a.va + yv, nb_val, &s_full[s], pol_stream);
                 tma_load_1d(stage_ro(s), a.ro + rb, nb_ro, &s_full[s], pol_stream);
-                lo = hi;
             }
+            lo = hi;
         }
     } else {
         // =============================== consumer warps ==========================================
         // The producer above streams the (immutable) matrix right away; x and y belong to the previous
         // kernel until it has completed.
         if constexpr (DOT) { griddep_wait(); griddep_launch_dependents(); }
+        if (tid == 0) {   // for the epilogue; the loads complete in the shadow of the first tile's arrival
+            const int e0 = a.tile_xy[min(t0, a.num_tiles)].x, e1 = a.tile_xy[min(t1, a.num_tiles)].x;
+            const int e2 = a.tile_xy[min(t1 + a.tiles_per_cta, a.num_tiles)].x;
+            s_edge[0] = e0; s_edge[1] = e1; s_edge[2] = e2;
+        }
         bool halo_ready = false;
         // general tiles: L2 priorities of the x gathers and the y stores (debug_flags bit 3: x evict-last, y evict-first)
         const uint64_t pol_x = (a.debug_flags & 8) ? l2_policy_evict_last() : l2_policy_evict_normal();
@@ -763,7 +784,7 @@ spmv_kernel(SpmvArgs<V> a, CgScalars cg)
     V dot_carry = 0;
     if (tid == 0 && t1 > t0 && !(a.debug_flags & 1)) {
         const int c = blockIdx.x;
-        const int r0 = a.tile_xy[t0].x, r1 = a.tile_xy[t1].x;   // rows in progress at the start / end of this CTA
+        const int r0 = s_edge[0], r1 = s_edge[1], r2 = s_edge[2];   // rows in progress at the start / end of this CTA, end of the next
         const bool has_in = c > 0 && r0 < a.m;
         const V out = s_running;                                  // leading part of row r1 seen by this CTA
         if constexpr (DOT) { if (r1 < a.m) dot_carry = out * __ldg(a.x + r1); }
@@ -774,12 +795,12 @@ spmv_kernel(SpmvArgs<V> a, CgScalars cg)
                 const V other = slot_exchange<V>(a.cta_slot + (c - 1), mine);
                 if (!is_sentinel<V>(other)) { slot_reset<V>(a.cta_slot + (c - 1)); a.y[r0] = mine + other; }
             }
-            cta_carry_publish<V>(a.tile_xy, a.tiles_per_cta, a.num_tiles, a.m, a.cta_slot, a.y, c, out);
+            cta_carry_publish<V>(a.tile_xy, a.tiles_per_cta, a.num_tiles, a.m, a.cta_slot, a.y, c, out, r1, r2);
         } else if (has_in) {   // the whole CTA lies inside row r0 == r1: pass the carry on
             const V other = slot_exchange<V>(a.cta_slot + (c - 1), out);
-            if (!is_sentinel<V>(other)) { slot_reset<V>(a.cta_slot + (c - 1)); cta_carry_publish<V>(a.tile_xy, a.tiles_per_cta, a.num_tiles, a.m, a.cta_slot, a.y, c, other + out); }
+            if (!is_sentinel<V>(other)) { slot_reset<V>(a.cta_slot + (c - 1)); cta_carry_publish<V>(a.tile_xy, a.tiles_per_cta, a.num_tiles, a.m, a.cta_slot, a.y, c, other + out, r1, r2); }
         } else {
-            cta_carry_publish<V>(a.tile_xy, a.tiles_per_cta, a.num_tiles, a.m, a.cta_slot, a.y, c, out);
+            cta_carry_publish<V>(a.tile_xy, a.tiles_per_cta, a.num_tiles, a.m, a.cta_slot, a.y, c, out, r1, r2);
         }
     }
 
