@@ -506,7 +506,10 @@ int launch_spmm_rows_t(smle_csr_t a, const V *X, V *Y, int k, const CgScalars &c
         int carve = 100;
         for (int kb : {8, 16, 32, 64, 100, 132, 164, 196, 228})
             if (need <= (size_t)kb * 1024) { carve = (kb * 100 + 227) / 228; break; }
-        CU(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
+        // SMLE_SPMM_CARVE: -1 (default) the smallest carve-out that fits, 0 leave the choice to the driver, else percent
+        const int carve_env = env_int("SMLE_SPMM_CARVE", -1);
+        if (carve_env > 0) carve = carve_env;
+        if (carve_env != 0) CU(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
         CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, THREADS + 32, smem));
         if (occ < 1) return fail(SMLE_ERR_CUDA, "spmm_rows_kernel does not fit on an SM (%zu B smem)", smem);
         if (occ > MINB) occ = MINB;
@@ -683,6 +686,7 @@ int launch_spmm_rows(smle_csr_t a, const V *X, V *Y, int k, const CgScalars &cg,
     if (cfg == spmm_cfg_id(th, tl, st, mb, ub, nv)) return launch_spmm_rows_t<V, G / nv, VEC, nv, ub, th, tl, st, mb, DOT>(a, X, Y, k, cg, dry);
             SMLE_CFG(960, 1920, 2, 1, 4, 1) SMLE_CFG(960, 2048, 2, 1, 4, 1) SMLE_CFG(960, 1920, 2, 1, 8, 1)
             SMLE_CFG(480, 2048, 2, 2, 4, 1) SMLE_CFG(224, 512, 2, 4, 4, 1) SMLE_CFG(960, 1920, 2, 1, 4, 2)
+            SMLE_CFG(960, 1920, 2, 1, 2, 2) SMLE_CFG(960, 1920, 2, 1, 3, 2)
 #undef SMLE_CFG
             return fail(SMLE_ERR_ARG, "unsupported SMLE_SPMM_CFG");
         }

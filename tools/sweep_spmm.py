@@ -38,6 +38,8 @@ for spec in sys.argv[3:] or ["256x1024x2x2@2"]:
         env["SMLE_SPMM_BAND"] = "1"
         if spec[4:]:
             env["SMLE_SPMM_BAND_CHUNK"] = spec[4:]
+    elif spec.startswith("carve"):       # default configuration, shared-memory carve-out: carve0 = driver's choice, carve<pct>
+        env["SMLE_SPMM_CARVE"] = spec[5:]
     elif spec in ("sched0", "sched1"):   # default configuration without / with the structure-aware tile schedule
         env["SMLE_SPMM_SCHED"] = spec[-1]
     else:
