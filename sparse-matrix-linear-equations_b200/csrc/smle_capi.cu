@@ -863,7 +863,7 @@ int launch_spmv(smle_csr_t a, const V *x, V *y, const CgScalars &cg, bool dry)
         SMLE_CFG(480, 4, 3) SMLE_CFG(480, 3, 4) SMLE_CFG(320, 6, 3) SMLE_CFG(640, 6, 2)
 #undef SMLE_CFG
 #define SMLE_CFG1(th, i, st) case 10000000 + th * 10000 + i * 100 + st: return launch_spmv_t<V, th, i, st, DOT, 1>(a, x, y, cg, dry);
-        SMLE_CFG1(640, 6, 2) SMLE_CFG1(480, 6, 2) SMLE_CFG1(640, 9, 2) SMLE_CFG1(480, 8, 2) SMLE_CFG1(960, 6, 2) SMLE_CFG1(320, 12, 2)
+        SMLE_CFG1(640, 6, 2) SMLE_CFG1(480, 6, 2) SMLE_CFG1(480, 8, 2)   // (640x9x2, 960x6x2, 320x12x2, 960x3x2, 960x2x2, 640x4x2 were measured and dropped: profiles/r02_spmv_skewed_cfg.txt)
 #undef SMLE_CFG1
     }
     return fail(SMLE_ERR_ARG, "unsupported SMLE_SPMV_CFG");

@@ -341,25 +341,28 @@ __device__ __forceinline__ V warp_sum_parts(const V *parts, int n, int lane)
 // row (owner part + carry); if CTA c+1 lies entirely inside the row, add its part and move on.
 template <typename V>
 __device__ __noinline__ void cta_carry_publish(const int2 *__restrict__ tile_xy, int tiles_per_cta, int num_tiles, int m,
-                                               V *cta_slot, V *y, int c, V val, int row_first, int next_first)
+                                               V *cta_slot, V *y, int c, V val, int row, int next)
 {
-    // row_first / next_first: the rows in progress at the end of CTA c and of CTA c+1, read by the caller at
-    // kernel start (the epilogue of a 20 us launch should not wait for two more dependent L2 round trips)
-    for (bool first = true;; first = false) {
-        const int row = first ? row_first : tile_xy[min((c + 1) * tiles_per_cta, num_tiles)].x;
-        if (row >= m) return;
+    // row / next: the rows in progress at the end of CTA c and of CTA c+1, read by the caller at kernel start
+    // (the epilogue of a 20 us launch should not wait for two more dependent L2 round trips).  While the carry
+    // is passed through CTAs that lie inside one row (the wheel's hub spans 49 of them), the row stays the
+    // same and a link costs one atomic exchange: the end row of the CTA after next is requested before the
+    // exchange, and the fence is needed only in front of the final store (64 -> ~17 us of serial tail).
+    if (row >= m) return;
+    for (;;) {
         V *slot = cta_slot + c;
+        const int next2 = tile_xy[min((c + 3) * tiles_per_cta, num_tiles)].x;
         const V owner = slot_exchange<V>(slot, val);
         if (is_sentinel<V>(owner)) return;                 // the other party comes later and finishes
         slot_reset<V>(slot);
-        __threadfence();                                   // its earlier stores to y[row] come before ours
-        const int next = first ? next_first : tile_xy[min((c + 2) * tiles_per_cta, num_tiles)].x;
         if (next > row) {                                  // the row ends in CTA c+1
+            __threadfence();                               // its earlier stores to y[row] come before ours
             y[row] = owner + val;
             return;
         }
         val = val + owner;                                 // CTA c+1 lies inside the row: pass on
         ++c;
+        next = next2;
     }
 }
 
