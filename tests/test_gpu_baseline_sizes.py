@@ -218,4 +218,8 @@ def test_rmat_20_general_tiles_one_cta_configuration(gpu, orc, dtype, tol):
     y = a.spmv(x)
     gold = orc.spmv_gold(ro, ci, va, x)
     assert rel_rownorm_err(y, gold, (ro, ci, va), x) <= tol
+    # the path is deterministic by construction (fixed summation trees, wait-free but order-independent carries):
+    # a race in the double / triple buffered shared-memory queues would show up as a run-to-run difference
+    for _ in range(8):
+        assert np.array_equal(a.spmv(x), y)
     a.close()
