@@ -811,16 +811,18 @@ int spmv_cfg()   // threads*10000 + ipt*100 + stages (+ 10000000 * CTAs-per-SM c
 bool spmv_cfg_forced() { return getenv("SMLE_SPMV_CFG") != nullptr; }
 
 constexpr int kSpmvCfgSmall = 480 * 10000 + 4 * 100 + 3;                 // 480x4x3
-constexpr int kSpmvCfgSkewed = 10000000 + 640 * 10000 + 6 * 100 + 2;     // 640x6x2, one CTA per SM
+constexpr int kSpmvCfgSkewed = 20000000 + 480 * 10000 + 4 * 100 + 2;     // 480x4x2, two CTAs per SM
 
 // The configuration of the single-vector kernel for this matrix (cached on the handle):
 //   * SMLE_SPMV_CFG when set;
 //   * small problems (fewer than ~16 default tiles per CTA, e.g. grid2d 1000^2: 7): tiles of 1920 items in 3
 //     stages start the first row sooner and drain faster (profiles/r02_spmv_grid2d_1000_cfg_sweep.jsonl);
-//   * skewed matrices (a quarter of the default tiles or more hold a row segment longer than kRowPathMaxLen:
-//     R-MAT, the wheel): one CTA per SM with tiles of 3840 items -- the scattered x gathers of such matrices
-//     live on L1 capacity, and one CTA's stages leave L1 ~92 KB where two leave ~28 KB (R-MAT scale 23
-//     1.40 -> 1.04 ms, scale 24 3.91 -> 2.53 ms; profiles/r02_spmv_skewed_cfg.txt);
+//   * skewed fp64 matrices (half of the default tiles or more hold a row segment longer than kRowPathMaxLen:
+//     R-MAT; the wheel, a third, is as fast on the default): two CTAs per SM with two stages of 1920 items each -- the scattered
+//     x gathers of such matrices ask one L2 slice for the same few hot lines, and what L1 absorbs never gets
+//     there: 76 KB of stages per CTA leave L1 ~92 KB where the default's 107 KB leave ~28 KB (R-MAT scale 22 /
+//     23 / 24: 626 / 1400 / 3906 -> 508 / 907 / 2123 us; one CTA of 640 threads with the same L1: 536 / 1029 /
+//     2521; profiles/r02_spmv_skewed_cfg.txt);
 //   * else 480x6x2.
 int spmv_pick(smle_csr_t a, int *cfg)
 {
@@ -835,7 +837,9 @@ int spmv_pick(smle_csr_t a, int *cfg)
             if (rc) return rc;
             static int skew_on = -1;
             if (skew_on < 0) skew_on = env_int("SMLE_SPMV_SKEWED_CFG", 1);
-            if (skew_on && (long long)p->general_tiles * 4 >= p->num_tiles) c = kSpmvCfgSkewed;
+            // fp64 only: the fp32 stages are half as large, two CTAs already leave L1 ~64 KB, and one CTA per SM
+            // measured slower there (R-MAT scale 24 fp32: 2.06 ms against 1.73)
+            if (skew_on && a->vbytes == 8 && (long long)p->general_tiles * 2 >= p->num_tiles) c = kSpmvCfgSkewed;
         }
     }
     a->spmv_cfg = *cfg = c;
@@ -865,6 +869,7 @@ int launch_spmv(smle_csr_t a, const V *x, V *y, const CgScalars &cg, bool dry)
 #define SMLE_CFG1(th, i, st) case 10000000 + th * 10000 + i * 100 + st: return launch_spmv_t<V, th, i, st, DOT, 1>(a, x, y, cg, dry);
         SMLE_CFG1(640, 6, 2) SMLE_CFG1(480, 6, 2) SMLE_CFG1(480, 8, 2)   // (640x9x2, 960x6x2, 320x12x2, 960x3x2, 960x2x2, 640x4x2 were measured and dropped: profiles/r02_spmv_skewed_cfg.txt)
 #undef SMLE_CFG1
+        case 20000000 + 480 * 10000 + 4 * 100 + 2: return launch_spmv_t<V, 480, 4, 2, DOT, 2>(a, x, y, cg, dry);   // 480x4x2x2
     }
     return fail(SMLE_ERR_ARG, "unsupported SMLE_SPMV_CFG");
 }

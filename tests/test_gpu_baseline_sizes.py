@@ -203,18 +203,18 @@ def test_interleaved_cg_spmm_cg_on_one_handle(gpu, orc):
     a.close()
 
 
-# ---- skewed matrices large enough for the one-CTA-per-SM configuration (R-MAT scale 20: 17.8 M merge items) ----
+# ---- skewed matrices large enough for the skewed-matrix configuration (R-MAT scale 20: 17.8 M merge items) ----
 @pytest.mark.parametrize("dtype,tol", [(np.float64, 1e-12), (np.float32, 1e-5)])
-def test_rmat_20_general_tiles_one_cta_configuration(gpu, orc, dtype, tol):
-    """R-MAT scale 20 x16: most tiles hold a row segment longer than 32, so the handle picks tiles of 3840 items
-    with one CTA per SM; every tier of the product-staged general path (thread / warp / CTA per segment, tiles
+def test_rmat_20_general_tiles_skewed_configuration(gpu, orc, dtype, tol):
+    """R-MAT scale 20 x16: most tiles hold a row segment longer than 32, so the fp64 handle picks two stages of
+    1920 items (more L1 for the scattered gathers; fp32 keeps tiles of 2880); every tier of the product-staged general path (thread / warp / CTA per segment, tiles
     inside one row) is exercised against the gold loop, componentwise in |A||x|."""
     ro, ci, va = gpu.gen_rmat(20, 16, seed=7, dtype=dtype)
     n = len(ro) - 1
     x = np.random.default_rng(3).random(n).astype(dtype)
     a = gpu.CsrMatrix(ro, ci, va, n)
     _, items = a.tile_coords(1)
-    assert items == 3840
+    assert items == (1920 if dtype == np.float64 else 2880)
     y = a.spmv(x)
     gold = orc.spmv_gold(ro, ci, va, x)
     assert rel_rownorm_err(y, gold, (ro, ci, va), x) <= tol
