@@ -13,11 +13,12 @@
 //   * regular tiles (no row segment longer than 32, every stencil): one thread per row straight from
 //     the stage buffers -- adjacent lanes own adjacent rows, so a warp's gathers of x fall into 2-3
 //     cache lines and y is written coalesced; no CTA-wide barrier, warps drift across tiles;
-//   * general tiles (R-MAT hubs, the wheel's spoke row): the same pass for the short rows; rows of
-//     33..1024 nonzeros are queued and dealt to the warps dynamically (lanes stride over the row,
-//     shuffle tree; one barrier per such tile), the rare longer segment (at most two per tile) is
-//     reduced by the whole CTA; the classic per-thread merge walk with its three barriers per tile
-//     and its bank conflicts is gone;
+//   * general tiles (R-MAT hubs, the wheel's hub row): product-staged -- every thread requests the x of
+//     IPT nonzeros at once, the products replace the staged values, and after one barrier the rows are
+//     summed from shared memory: up to 32 nonzeros by a thread, up to 1024 by a warp taking rows from the
+//     tile's queue, longer segments by the whole CTA (one more barrier); a tile that lies inside one row
+//     keeps its products in registers.  The classic per-thread merge walk with its three barriers per
+//     tile and its bank conflicts is gone;
 //   * carries: per-tile -> per-CTA in shared memory; the row cut by a CTA boundary is finished
 //     wait-free through one global slot per boundary (the party that arrives second adds owner
 //     part + carry, merge_based.hpp:137-149 semantics), so a plain SpMV has no last-CTA epilogue;
@@ -263,9 +264,10 @@ __device__ __forceinline__ V strided_sum(const V *__restrict__ x, const int *pc,
 }
 
 // ---- general tiles, product-staged path ---------------------------------------------------------
-// The gather of x with an L2 cache hint in a register: evict-last when x is too large for the matrix
-// stream and the y stores to leave it alone (R-MAT scale 24: x = 134 MB against 126 MB of L2),
-// evict-normal otherwise.  Halo tiles (COH) keep the L2-coherent load.
+// The gather of x with an L2 cache hint in a register: evict-normal by default; SMLE_SPMV_DEBUG bit 3 asks
+// for evict-last gathers and evict-first y stores (R-MAT scale 24, x = 134 MB against 126 MB of L2: no
+// effect measured, profiles/r02_spmv_general_tiles_staged_ab.jsonl).  Halo tiles (COH) keep the
+// L2-coherent load.
 template <typename V, bool COH>
 __device__ __forceinline__ V gather_hint(const V *x, uint64_t pol)
 {
@@ -385,8 +387,9 @@ __device__ __noinline__ void cta_carry_publish(const int2 *__restrict__ tile_xy,
 // ---------------------------------------------------------------------------------------
 constexpr int kChainTiles = 512;   // tiles between two carry-chain resolutions of a CTA
 
-//   MAXB > 0 caps the CTAs per SM below what shared memory allows: skewed matrices run ONE CTA per SM, so that the
-//   carve-out leaves 90-150 KB of L1 to the scattered x gathers instead of ~28 KB (R-MAT scale 24: 3.9 -> 2.5 ms)
+//   MAXB > 0 caps the CTAs per SM below what shared memory allows (registers follow: 64 at two CTAs of 512
+//   threads, where three would get 40 and spill): the configuration for skewed matrices, 480x4x2 at two CTAs
+//   per SM, leaves ~92 KB of L1 to the scattered x gathers instead of ~28 KB (R-MAT scale 24: 3.9 -> 2.1 ms)
 template <typename V, int THREADS, int IPT, int STAGES, bool DOT, int MAXB = 0>
 __global__ void __launch_bounds__(THREADS + 32, (MAXB > 0 && MAXB < spmv_ctas_per_sm<V, THREADS, IPT, STAGES>())
                                                     ? MAXB : spmv_ctas_per_sm<V, THREADS, IPT, STAGES>())
@@ -564,7 +567,7 @@ spmv_kernel(SpmvArgs<V> a, CgScalars cg)
                 // indices), the products replace the staged values, and after ONE barrier the rows are summed from
                 // shared memory: <= med_lo by a thread, <= kWarpRowMax by a warp taking rows from the tile's queue,
                 // longer segments by the whole CTA.  A tile that lies inside one row (a hub row spans many tiles)
-                // never writes its products back: thread sums -> warp sums -> thread 0.
+                // never writes its products back: thread sums -> warp sums -> warp 0.
                 const int qc = gen_count % 3, qn = (gen_count + 1) % 3, hp = gen_count & 1;
                 ++gen_count;
                 if (tid == 0) { s_nlong[qn] = 0; s_next[qn] = 0; s_nhq[qn] = 0; }
