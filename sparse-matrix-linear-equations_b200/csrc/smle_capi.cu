@@ -870,6 +870,7 @@ int launch_spmv(smle_csr_t a, const V *x, V *y, const CgScalars &cg, bool dry)
         SMLE_CFG1(640, 6, 2) SMLE_CFG1(480, 6, 2) SMLE_CFG1(480, 8, 2)   // (640x9x2, 960x6x2, 320x12x2, 960x3x2, 960x2x2, 640x4x2 were measured and dropped: profiles/r02_spmv_skewed_cfg.txt)
 #undef SMLE_CFG1
         case 20000000 + 480 * 10000 + 4 * 100 + 2: return launch_spmv_t<V, 480, 4, 2, DOT, 2>(a, x, y, cg, dry);   // 480x4x2x2
+        case 20000000 + 480 * 10000 + 3 * 100 + 2: return launch_spmv_t<V, 480, 3, 2, DOT, 2>(a, x, y, cg, dry);   // 480x3x2x2
     }
     return fail(SMLE_ERR_ARG, "unsupported SMLE_SPMV_CFG");
 }
