@@ -869,8 +869,7 @@ int launch_spmv(smle_csr_t a, const V *x, V *y, const CgScalars &cg, bool dry)
 #define SMLE_CFG1(th, i, st) case 10000000 + th * 10000 + i * 100 + st: return launch_spmv_t<V, th, i, st, DOT, 1>(a, x, y, cg, dry);
         SMLE_CFG1(640, 6, 2) SMLE_CFG1(480, 6, 2) SMLE_CFG1(480, 8, 2)   // (640x9x2, 960x6x2, 320x12x2, 960x3x2, 960x2x2, 640x4x2 were measured and dropped: profiles/r02_spmv_skewed_cfg.txt)
 #undef SMLE_CFG1
-        case 20000000 + 480 * 10000 + 4 * 100 + 2: return launch_spmv_t<V, 480, 4, 2, DOT, 2>(a, x, y, cg, dry);   // 480x4x2x2
-        case 20000000 + 480 * 10000 + 3 * 100 + 2: return launch_spmv_t<V, 480, 3, 2, DOT, 2>(a, x, y, cg, dry);   // 480x3x2x2
+        case 20000000 + 480 * 10000 + 4 * 100 + 2: return launch_spmv_t<V, 480, 4, 2, DOT, 2>(a, x, y, cg, dry);   // 480x4x2x2   (480x3x2x2, stages of 1440 items and L1 ~124 KB: 980 / 2154 us at scale 23 / 24 against 907 / 2123 -- dropped)
     }
     return fail(SMLE_ERR_ARG, "unsupported SMLE_SPMV_CFG");
 }
