@@ -139,7 +139,7 @@ def run_multicg(args):
 def run_stress(args):
     torch, S, st = _setup()
     peak = _peak()
-    scale = int(os.environ.get("SMLE_RMAT_SCALE", "22"))
+    scale = int(os.environ.get("SMLE_RMAT_SCALE", "24"))   # configs[3] names scale 24 / 2^24; smaller for quick runs
     with torch.cuda.stream(st):
         for mname, gen in ((f"rmat scale {scale} x16", lambda dt: S.gen_rmat(scale, 16, seed=42, dtype=dt)),
                            (f"wheel 2^{scale}", lambda dt: S.gen_wheel(1 << scale, 1.0, dt))):
